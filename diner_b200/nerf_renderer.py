@@ -1,0 +1,71 @@
+"""NeRFRendererDGS with the reference's constructor, mutable attributes and forward() contract
+(src/models/nerf_renderer.py:23-37,399-430), served by libdiner_b200.
+
+`n_samples` / `n_gaussian` are read at call time because the reference CLI reassigns them on the live
+module (python_scripts/create_prediction_folder.py:44-47)."""
+import torch
+
+try:                                    # the reference returns dotmap.DotMap; use it when installed
+    from dotmap import DotMap
+except Exception:                       # same attribute-access contract without the dependency
+    class DotMap(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError as e:
+                raise AttributeError(k) from e
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+
+class NeRFRendererDGS(torch.nn.Module):
+    def __init__(self, n_samples=40, n_depth_candidates=1000, n_gaussian=15, eval_batch_size=100000,
+                 white_bkgd=True):
+        super().__init__()
+        self.n_samples = n_samples
+        self.n_depth_candidates = n_depth_candidates
+        self.n_gaussian = n_gaussian
+        self.eval_batch_size = eval_batch_size      # kept for API parity; the fused kernels need no chunking
+        self.white_bkgd = white_bkgd
+        self.noise = None   # optional dict(u_coarse, g_noise, u_fill, seed): injected draws (tests) / seed
+        self._calls = 0
+
+    def _noise_for_call(self):
+        if self.noise is not None:
+            return self.noise
+        self._calls += 1
+        return dict(seed=(torch.initial_seed() * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF)
+
+    @torch.no_grad()
+    def sample_depthguided(self, rays, model, n_samples, n_candidates, depth_diff_max=0.05, n_gaussian=None):
+        """Depth-guided shortlist, nerf_renderer.py:65-190.  Returns (SB,NR,n_samples) with 0 = empty slot,
+        sorted ascending (the reference returns the same multiset ordered by likelihood)."""
+        if depth_diff_max != 0.05:
+            raise NotImplementedError("depth_diff_max is fixed to the reference default 0.05")
+        G = self.n_gaussian if n_gaussian is None else n_gaussian
+        assert n_samples >= G
+        _, zd = model.context().sample(rays.float().contiguous(), n_samples, n_candidates, G,
+                                       self._noise_for_call(), want_dgs=True)
+        return zd
+
+    def composite(self, model, rays, z_samp):
+        """nerf_renderer.py:286-365 -> (weights (SB,B,K), rgb (SB,B,3), depth (SB,B))."""
+        model._no_grad_only(rays, z_samp)
+        return model.context().composite(rays.float().contiguous(), z_samp.float().contiguous(), self.white_bkgd,
+                                         model.mode_id(), want_weights=True)
+
+    def forward(self, model, rays, want_weights=False):
+        """rays (SB,B,8) [origin3, dir3, near, far] -> DotMap(fine=DotMap(rgb (SB,B,3), depth (SB,B)[, weights]))."""
+        assert len(rays.shape) == 3
+        model._no_grad_only(rays)
+        rgb, depth, w, _ = model.context().render(
+            rays.float().contiguous(), int(self.n_samples), int(self.n_depth_candidates), int(self.n_gaussian),
+            self.white_bkgd, model.mode_id(), self._noise_for_call(), want_weights=want_weights)
+        return DotMap(fine=self._format_outputs(w, rgb, depth, want_weights))
+
+    def _format_outputs(self, weights, rgb, depth, want_weights):
+        out = DotMap(rgb=rgb, depth=depth)
+        if want_weights:
+            out.weights = weights
+        return out

@@ -1,0 +1,120 @@
+/* libdiner_b200 -- C ABI of the B200-native DINER volumetric-rendering hot path.
+ *
+ * The reference (malteprinzler/diner) is pure Python/PyTorch and has no FFI of its own; its plugin
+ * boundary for this path is the pair of nn.Modules resolved by import_obj (src/util/import_helper.py:16-24)
+ * at src/models/diner.py:47-48:
+ *     src.models.nerf_renderer.NeRFRendererDGS   (configs/train_dtu.yaml:53)
+ *     src.models.pixelnerf.PixelNeRF             (configs/train_dtu.yaml:32)
+ * The entry points below are what those modules' methods bind through ctypes (diner_b200/capi.py);
+ * each one names the reference method / lines it replaces.  Plain pointers and sizes only, no torch
+ * types.  Unless a function is suffixed _host, every pointer is caller-owned DEVICE memory
+ * (contiguous fp32) that must stay valid until the work queued on `stream` has completed; `stream`
+ * is a cudaStream_t passed as void* (0 = default stream).
+ *
+ * Every function returns 0 on success and a negative DINER_E_* code on failure; the message is
+ * available from diner_last_error() (thread-local).  Nothing throws across the boundary.
+ * One call in flight per context (no internal locking).
+ */
+#ifndef DINER_B200_H
+#define DINER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DINER_OK 0
+#define DINER_E_INVALID (-1)      /* bad argument / unsupported shape */
+#define DINER_E_CUDA (-2)         /* CUDA runtime error (message has the cudaError string) */
+#define DINER_E_STATE (-3)        /* call order: weights / scene not set */
+#define DINER_E_UNSUPPORTED (-4)  /* valid request the selected mode cannot serve */
+
+/* Arithmetic mode of the per-sample MLP (ResnetFC). */
+#define DINER_MODE_FP32 0     /* CUDA-core fp32 FMA: reference arithmetic, slow; parity anchor            */
+#define DINER_MODE_PARITY 1   /* tcgen05 bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accum): <=1e-4 vs fp32 */
+#define DINER_MODE_FAST 2     /* tcgen05 single-pass bf16, fp32 accum: PSNR-level agreement only          */
+
+typedef struct diner_ctx diner_ctx;
+
+const char* diner_last_error(void);
+int diner_version(void);
+
+/* Creates a context on CUDA device `device` (must be sm_100). */
+int diner_create(diner_ctx** out, int device);
+void diner_destroy(diner_ctx* ctx);
+
+/* ResnetFC parameters -- replaces reading nerf.mlp_fine.* inside ResnetFC.forward (src/models/resnetfc.py:129-159).
+ * Layout exactly as the reference state_dict: weight (out,in) row-major + bias (out).
+ *   lin_in (d_hidden,d_in)  lin_out (d_out,d_hidden)
+ *   fc0[b], fc1[b] (d_hidden,d_hidden) for b < n_blocks      (blocks.b.fc_0 / fc_1)
+ *   lin_z[b] (d_hidden,d_latent)       for b < min(combine_layer,n_blocks)
+ * The library keeps its own packed copies; call again whenever the parameters change. */
+int diner_set_mlp(diner_ctx* ctx, int d_in, int d_latent, int d_hidden, int d_out, int n_blocks,
+                  int combine_layer, const float* lin_in_w, const float* lin_in_b, const float* lin_out_w,
+                  const float* lin_out_b, const float* const* fc0_w, const float* const* fc0_b,
+                  const float* const* fc1_w, const float* const* fc1_b, const float* const* lin_z_w,
+                  const float* const* lin_z_b, void* stream);
+
+/* Scene state -- replaces what PixelNeRF.encode leaves on the modules (src/models/pixelnerf.py:44-51,
+ * src/models/image_encoder.py:232-237,290-291):
+ *   latent  (SB,NV,L,Hl,Wl) NCHW fp32 as the reference stores it (re-laid out to NHWC internally)
+ *   depths, depths_std (SB,NV,1,H,W); normals (SB,NV,3,H,W)
+ *   poses (SB,NV,4,4) world->cam; focal, c (SB,NV,2); image is W x H pixels
+ *   feature_padding = image_padding / conv1 stride (image_encoder.py:58); num_freqs / freq_factor of
+ *   the PositionalEncoding (src/models/positional_encoding.py:14-31). */
+int diner_set_scene(diner_ctx* ctx, int SB, int NV, int L, int Hl, int Wl, int H, int W, const float* latent,
+                    const float* depths, const float* depths_std, const float* normals, const float* poses,
+                    const float* focal, const float* c, float feature_padding, int num_freqs,
+                    float freq_factor, void* stream);
+
+/* Optional injected noise (dense, indexed by logical position); any pointer may be NULL, in which
+ * case counter-based noise derived from `seed` is used for that draw.
+ *   u_coarse (SB,NR,C) U[0,1)  -> torch.rand_like  at nerf_renderer.py:57
+ *   g_noise  (SB,NR,G) N(0,1)  -> torch.randn_like at nerf_renderer.py:188
+ *   u_fill   (SB,NR,K) U[0,1)  -> torch.rand_like  at nerf_renderer.py:390 (by column after the sort) */
+typedef struct diner_noise {
+    const float* u_coarse;
+    const float* g_noise;
+    const float* u_fill;
+    uint64_t seed;
+} diner_noise;
+
+/* NeRFRendererDGS.forward (src/models/nerf_renderer.py:399-424): rays (SB,NR,8) = [o3,d3,near,far] ->
+ * rgb (SB,NR,3), depth (SB,NR); weights (SB,NR,K) and z (SB,NR,K) are optional outputs (NULL to skip).
+ * K = n_samples, C = n_depth_candidates, G = n_gaussian are read per call because the reference CLI
+ * mutates them on the live module (python_scripts/create_prediction_folder.py:44-47). */
+int diner_render(diner_ctx* ctx, const float* rays, int SB, int NR, int K, int C, int G, int white_bkgd,
+                 int mode, const diner_noise* noise, float* rgb, float* depth, float* weights, float* z,
+                 void* stream);
+
+/* Same call with HOST buffers (rays in, rgb/depth out): copies host->device, renders, copies back and
+ * synchronises the stream.  This is the end-to-end entry a non-torch caller uses. */
+int diner_render_host(diner_ctx* ctx, const float* rays_host, int SB, int NR, int K, int C, int G,
+                      int white_bkgd, int mode, uint64_t seed, float* rgb_host, float* depth_host,
+                      void* stream);
+
+/* Stage entry points (used by the module methods and the stage-wise parity tests). */
+/* sample_depthguided + fill_up_uniform_samples (nerf_renderer.py:65-190, :367-397) -> z (SB,NR,K) ascending;
+ * z_dgs (optional): depth-guided result before the fill, ascending, 0 = empty slot. */
+int diner_sample(diner_ctx* ctx, const float* rays, int SB, int NR, int K, int C, int G,
+                 const diner_noise* noise, float* z, float* z_dgs, void* stream);
+/* PixelNeRF.forward (src/models/pixelnerf.py:55-145): xyz, viewdirs (SB,B,3) -> out (SB,B,4). */
+int diner_query(diner_ctx* ctx, const float* xyz, const float* viewdirs, int SB, long long B, int mode,
+                float* out, void* stream);
+/* NeRFRendererDGS.composite (nerf_renderer.py:286-365) on given sample depths z (SB,NR,K). */
+int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, int NR, int K, int white_bkgd,
+                    int mode, float* rgb, float* depth, float* weights, void* stream);
+
+/* Number of kernels this library launched on behalf of ctx since creation (bench.py's gpu_launches). */
+long long diner_launch_count(diner_ctx* ctx);
+/* Device time in ms of the MLP kernels of the last render/composite/query call when timing was
+ * enabled with diner_set_timing(ctx, 1) (CUDA events on the caller's stream; forces a sync). */
+int diner_set_timing(diner_ctx* ctx, int enabled);
+float diner_last_mlp_ms(diner_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINER_B200_H */

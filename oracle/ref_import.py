@@ -49,7 +49,11 @@ def load():
     saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
     for k in saved:
         del sys.modules[k]
-    sys.path.insert(0, REF_ROOT)
+    # the reference's `src` is a namespace package (no __init__.py); a regular `src` package anywhere on
+    # sys.path (this repo's shim) would win over it, so hide those entries while importing
+    old_path = list(sys.path)
+    sys.path[:] = [REF_ROOT] + [p for p in old_path
+                               if not os.path.exists(os.path.join(p or os.getcwd(), "src", "__init__.py"))]
     try:
         import importlib
         ns = types.SimpleNamespace()
@@ -62,7 +66,7 @@ def load():
         ns.cam_geometry = importlib.import_module("src.util.cam_geometry")
         ns.depth2normal = importlib.import_module("src.util.depth2normal")
     finally:
-        sys.path.remove(REF_ROOT)
+        sys.path[:] = old_path
         ref_mods = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
         for k in ref_mods:
             del sys.modules[k]
