@@ -38,6 +38,7 @@ SIGNATURES = {
     "diner_sample": (_I, [_P, _P, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
     "diner_query": (_I, [_P, _P, _P, _I, _LL, _I, _P, _P]),
     "diner_composite": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "diner_set_option": (_I, [_P, ctypes.c_char_p, _LL]),
     "diner_launch_count": (_LL, [_P]),
     "diner_set_timing": (_I, [_P, _I]),
     "diner_last_mlp_ms": (_F, [_P]),
@@ -95,6 +96,9 @@ class Context:
         self._check(self.lib.diner_create(ctypes.byref(h), idx))
         self.handle = h
         self._keep = []
+        for key, env in (("cluster", "DINER_TC_CLUSTER"), ("sub_batch", "DINER_TC_SUB_BATCH")):
+            if os.environ.get(env):
+                self.set_option(key, int(os.environ[env]))
 
     def _check(self, rc):
         if rc != 0:
@@ -216,6 +220,9 @@ class Context:
                 self.handle, ctypes.c_void_p(rays_host.data_ptr()), SB, NR, K, C, G, int(bool(white_bkgd)), mode,
                 int(seed), ctypes.c_void_p(rgb_host.data_ptr()), ctypes.c_void_p(depth_host.data_ptr()),
                 _stream(self.device)))
+
+    def set_option(self, key, value):
+        self._check(self.lib.diner_set_option(self.handle, key.encode(), int(value)))
 
     def launch_count(self):
         return int(self.lib.diner_launch_count(self.handle))

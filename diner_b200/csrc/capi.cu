@@ -362,6 +362,20 @@ extern "C" int diner_render_host(diner_ctx* c, const float* rays_host, int SB, i
     return DINER_OK;
 }
 
+extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) {
+    if (!c || !key) return fail(DINER_E_INVALID, "NULL ctx / key");
+    if (!strcmp(key, "cluster")) {
+        if (value != 1 && value != 2 && value != 4) return fail(DINER_E_INVALID, "cluster must be 1, 2 or 4");
+        c->tc.cluster = (int)value;
+    } else if (!strcmp(key, "sub_batch")) {
+        if (value < 64) return fail(DINER_E_INVALID, "sub_batch must be >= 64");
+        c->tc.sub_batch = value;
+    } else {
+        return fail(DINER_E_INVALID, "unknown option '%s'", key);
+    }
+    return DINER_OK;
+}
+
 extern "C" long long diner_launch_count(diner_ctx* c) { return c ? c->launches : 0; }
 extern "C" int diner_set_timing(diner_ctx* c, int enabled) {
     if (!c) return fail(DINER_E_INVALID, "ctx is NULL");

@@ -12,6 +12,12 @@ struct TcState {
     void* scratch = nullptr;      // combined activations x_c between the pre- and post-combine kernels
     size_t scratch_bytes = 0;
     int* err_flag = nullptr;      // device-side watchdog flag (mbarrier timeouts)
+    int n_pre = 0, n_post = 0;    // ResnetFC blocks before / after the view-combine
+    int pairs_pre = 0, pairs_post = 0;   // (hi,lo) weight tile pairs per CTA tile of the PRE / POST kernel
+    size_t bias_post_off = 0;
+    int cluster = 1;              // thread-block cluster size for weight multicast (1, 2 or 4)
+    long long sub_batch = 0;      // samples per PRE/POST launch pair (0 = default)
+    int max_grid[3] = {0, 0, 0};  // co-resident CTAs for cluster sizes 1, 2, 4 (queried lazily)
 };
 
 cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st);

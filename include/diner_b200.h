@@ -107,6 +107,10 @@ int diner_query(diner_ctx* ctx, const float* xyz, const float* viewdirs, int SB,
 int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, int NR, int K, int white_bkgd,
                     int mode, float* rgb, float* depth, float* weights, void* stream);
 
+/* Tuning knobs of the tcgen05 path (not part of the reference API): key = "cluster" (thread-block cluster size for
+ * weight multicast: 1, 2 or 4) or "sub_batch" (samples per PRE/POST launch pair). */
+int diner_set_option(diner_ctx* ctx, const char* key, long long value);
+
 /* Number of kernels this library launched on behalf of ctx since creation (bench.py's gpu_launches). */
 long long diner_launch_count(diner_ctx* ctx);
 /* Device time in ms of the MLP kernels of the last render/composite/query call when timing was
