@@ -1,0 +1,272 @@
+"""Benchmark of the DINER render hot path (BASELINE.json metric: rays/s at 512x512, 4 source views,
+64 samples/ray).  One "step" = NeRFRendererDGS.forward over the whole 512x512 target image
+(262 144 rays; depth-guided sampling -> feature projection/fusion -> positional encoding -> MLP ->
+compositing), scene encode excluded.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode parity|fast|fp32] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU): the rays of the image are split into N contiguous
+shards (strong scaling, BASELINE.json configs[3]), every rank renders its shard on a replicated scene
+and ONE NCCL all-gather of rgb|depth ends the step.  Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+import torch  # noqa: E402
+
+H = W = 512
+NV, K, C, G = 4, 64, 1000, int(15 * 64 / 40)
+NEAR, FAR = 0.3211, 1.2041                     # DTU: 400*s, 1500*s with s = 0.7/872
+WHITE = False
+SEED = 0
+FLOP_PER_SAMPLE = 4774912 * NV + 2101248       # algorithmic MLP FLOPs per sample
+FLOP_PRE_PER_SAMPLE = 4774912 * NV             # ... of which in the per-sample-view (PRE) kernel
+WORKLOAD = "DTU-shaped synthetic 512x512, 4 src views, 64 samples/ray, 1000 depth candidates, 24 gaussian"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def build_inputs():
+    from diner_b200 import synthetic as S
+    batch = S.make_scene(H, W, NV, 1, NEAR, FAR, SEED)
+    Hl, Wl = (H + 128) // 2, (W + 128) // 2
+    gen = torch.Generator().manual_seed(SEED)
+    latent = torch.randn(1, NV, 512, Hl, Wl, generator=gen) * 0.5          # 839 MB fp32 (stand-in for the ResNet pyramid)
+    mlp = S.make_mlp_state(seed=SEED)
+    rays = S.gen_rays(batch["target_extrinsics"], batch["target_intrinsics"], W, H,
+                      torch.full((1,), NEAR), torch.full((1,), FAR)).view(1, H * W, 8).contiguous()
+    return batch, latent, mlp, rays
+
+
+def cpu_baseline(batch, latent, mlp, rays, n_rays=1536, warm=256):
+    """The oracle port (torch-CPU restatement pinned to the reference) on this box's host cores, bounded sample."""
+    from oracle import diner_oracle as O
+    from diner_b200 import synthetic as S
+    scene = O.make_scene_state(batch, latent, mlp)
+    pick = torch.arange(n_rays) * (H * W // n_rays) + 131
+    r = rays[:, pick].contiguous()
+
+    def run(rr):
+        n = rr.shape[1]
+        return O.render(scene, rr, K, C, G, WHITE, S.hash_uniform((1, n, C), 1, 1), S.hash_normal((1, n, G), 1, 2),
+                        S.hash_uniform((1, n, K), 1, 3))
+    with torch.no_grad():
+        run(r[:, :warm])
+        t0 = time.time()
+        run(r)
+        dt = time.time() - t0
+    return dict(value=n_rays / dt, unit="rays/s", cores=torch.get_num_threads(), kind="port",
+                sample="%d rays of the 512x512 workload (strided), oracle/diner_oracle.py on torch-CPU fp32, %.1f s" % (n_rays, dt))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch, latent, mlp, rays = build_inputs()
+    n_rays = 1024
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(batch, latent, mlp, rays, n_rays=n_rays, warm=64 if i == 0 else 8)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    cb["sample"] = "each step = %d strided rays of the workload through oracle/diner_oracle.py (torch-CPU fp32 port of the reference; " \
+                   "the Python reference itself cannot travel to this box)" % n_rays
+    print(json.dumps({"impl": "reference", "metric": "rays_per_sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_rays / v,
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": {"workload": WORKLOAD},
+                      "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mode", default=os.environ.get("DINER_B200_MODE", "parity"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    from tests.common import product_model
+    from diner_b200.nerf_renderer import NeRFRendererDGS
+    batch, latent, mlp, rays = build_inputs()
+    model = product_model(batch, latent, mlp, dev, args.mode)
+    rend = NeRFRendererDGS(n_samples=K, n_depth_candidates=C, n_gaussian=G, white_bkgd=WHITE)
+    n_total = H * W
+    per = (n_total + world - 1) // world
+    lo, hi = rank * per, min(n_total, (rank + 1) * per)
+    rays_host = rays[:, lo:hi].contiguous().pin_memory()
+    rays_dev = rays_host.to(dev)
+    gathered = torch.empty(world, per, 4, device=dev) if world > 1 else None
+    mine = torch.zeros(per, 4, device=dev)
+    ctx = model.context()
+
+    def step(src):
+        with torch.no_grad():
+            out = rend(model, src)
+        if world > 1:                                   # one all-gather of rgb|depth per image
+            mine[:hi - lo, :3] = out.fine.rgb[0]
+            mine[:hi - lo, 3] = out.fine.depth[0]
+            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+        return out
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(rays_dev)
+    sync()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(rays_dev)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    # end-to-end: pinned host rays in, rgb + depth back on the host, every step
+    rgb_h = torch.empty(1, hi - lo, 3).pin_memory()
+    dep_h = torch.empty(1, hi - lo).pin_memory()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step(rays_host.to(dev, non_blocking=True))
+        rgb_h.copy_(out.fine.rgb, non_blocking=True)
+        dep_h.copy_(out.fine.depth, non_blocking=True)
+        torch.cuda.synchronize()
+    sync()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # per-kernel breakdown for the roofline: a separate short pass with CUDA-event timing inside the library
+    ctx.set_timing(True)
+    stage = {"sampler": 0.0, "mlp_pre": 0.0, "mlp_post": 0.0, "composite": 0.0}
+    nt = 2
+    for _ in range(nt):
+        step(rays_dev)
+        torch.cuda.synchronize()
+        for k_, v_ in ctx.last_stage_ms().items():
+            stage[k_] += v_ / nt
+    ctx.set_timing(False)
+
+    if rank == 0:
+        pk = peaks()
+        rays_per_s = n_total * args.steps / (ms * 1e-3)
+        n_samp_rank = (hi - lo) * K
+        n_pre_launches = -(-n_samp_rank // 524288)
+        pre_ms_per_launch = stage["mlp_pre"] / n_pre_launches if stage["mlp_pre"] > 0 else None
+        pre_flops_per_launch = FLOP_PRE_PER_SAMPLE * n_samp_rank / n_pre_launches
+        achieved = pre_flops_per_launch / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
+        line = {
+            "metric": "rays_per_sec", "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": {"parity": "bf16x3-split operands, f32 accumulate (1e-4 parity mode)", "fast": "bf16, f32 accumulate",
+                      "fp32": "f32"}[args.mode],
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "mode": args.mode, "rays_per_step": n_total, "sharding": "rays/%d" % world,
+                       "l2": "inputs larger than L2 (839 MB fp32 latent, 537 MB activations scratch per 524288 samples)",
+                       "cluster": int(os.environ.get("DINER_TC_CLUSTER", "1"))},
+            "e2e": {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                    "h2d_bytes_per_step": rays_host.numel() * 4 * world, "d2h_bytes_per_step": (rgb_h.numel() + dep_h.numel()) * 4 * world},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "tc::mlp_tc_kernel<PRE> (per sample-view ResnetFC layers)",
+                         "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["sustained"], "peak_source": pk["src"] + " bf16 dense sustained",
+                         "traffic": None,
+                         "whole_step_frac": rays_per_s / world * K * FLOP_PER_SAMPLE / 1e12 / pk["sustained"],
+                         "executed_flop_multiplier": 3 if args.mode == "parity" else 1,
+                         "stage_ms_per_step": stage},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(batch, latent, mlp, rays)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,9 +39,11 @@ SIGNATURES = {
     "diner_query": (_I, [_P, _P, _P, _I, _LL, _I, _P, _P]),
     "diner_composite": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "diner_set_option": (_I, [_P, ctypes.c_char_p, _LL]),
+    "diner_debug_sync": (_I, [_P]),
     "diner_launch_count": (_LL, [_P]),
     "diner_set_timing": (_I, [_P, _I]),
     "diner_last_mlp_ms": (_F, [_P]),
+    "diner_last_stage_ms": (_F, [_P, _I]),
 }
 
 _lib = None
@@ -224,11 +226,19 @@ class Context:
     def set_option(self, key, value):
         self._check(self.lib.diner_set_option(self.handle, key.encode(), int(value)))
 
+    def debug_sync(self):
+        self._check(self.lib.diner_debug_sync(self.handle))
+
     def launch_count(self):
         return int(self.lib.diner_launch_count(self.handle))
 
     def set_timing(self, enabled):
         self._check(self.lib.diner_set_timing(self.handle, int(enabled)))
+
+    def last_stage_ms(self):
+        """dict of device ms of the last call's stages (needs set_timing(True))."""
+        names = ("sampler", "mlp_pre", "mlp_post", "composite")
+        return {n: float(self.lib.diner_last_stage_ms(self.handle, i)) for i, n in enumerate(names)}
 
     def last_mlp_ms(self):
         return float(self.lib.diner_last_mlp_ms(self.handle))

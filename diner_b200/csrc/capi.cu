@@ -55,8 +55,8 @@ struct diner_ctx {
     TcState tc;                      // packed weights + scratch of the tcgen05 path
     long long launches = 0;
     int timing = 0;
-    float last_mlp_ms = 0.f;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_mlp_ms = 0.f, last_sampler_ms = 0.f, last_composite_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 };
 
 extern "C" const char* diner_last_error(void) { return g_err; }
@@ -80,6 +80,8 @@ extern "C" int diner_create(diner_ctx** out, int device) {
     CUDA_TRY(upload_std_ring_gain());
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaEventCreate(&c->ev2));
+    CUDA_TRY(cudaEventCreate(&c->ev3));
     *out = c;
     return DINER_OK;
 }
@@ -93,6 +95,8 @@ extern "C" void diner_destroy(diner_ctx* c) {
     if (c->host_pin) cudaFreeHost(c->host_pin);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
     delete c;
 }
 
@@ -221,7 +225,7 @@ static int run_query(diner_ctx* c, const QueryArgs& q, int mode, cudaStream_t st
             return fail(DINER_E_UNSUPPORTED, "tensor-core path unavailable for this MLP shape: %s", c->tc.why);
         cudaError_t e = tc_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st);
         if (e == cudaErrorNotSupported) return fail(DINER_E_UNSUPPORTED, "tensor-core path: %s", c->tc.why);
-        if (e != cudaSuccess) return fail(DINER_E_CUDA, "tc_query: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail(DINER_E_CUDA, "tc_query: %s (watchdog code %d)", cudaGetErrorString(e), c->tc.err_flag ? *c->tc.err_flag : -1);
     } else {
         return fail(DINER_E_INVALID, "unknown mode %d", mode);
     }
@@ -256,8 +260,14 @@ static int do_sample(diner_ctx* c, const float* rays, int SB, int NR, int K, int
     a.cstep = (float)(1.0 / (double)C);
     a.z_out = z; a.z_dgs = z_dgs;
     if (NR == 0) return DINER_OK;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev2, st));
     CUDA_TRY(launch_sampler(c->scene, a, c->num_sms, st));
     g_launches++;
+    if (c->timing) {
+        CUDA_TRY(cudaEventRecord(c->ev3, st));
+        CUDA_TRY(cudaEventSynchronize(c->ev3));
+        CUDA_TRY(cudaEventElapsedTime(&c->last_sampler_ms, c->ev2, c->ev3));
+    }
     return DINER_OK;
 }
 
@@ -266,6 +276,7 @@ extern "C" int diner_sample(diner_ctx* c, const float* rays, int SB, int NR, int
     int rc = check_ready(c);
     if (rc) return rc;
     if ((rc = check_render_args(c, SB, NR, K, C, G))) return rc;
+    if ((long long)SB * NR == 0) return DINER_OK;
     if (!rays || !z) return fail(DINER_E_INVALID, "NULL rays / z");
     CUDA_TRY(cudaSetDevice(c->device));
     const long long l0 = g_launches;
@@ -299,8 +310,14 @@ static int do_composite(diner_ctx* c, const float* rays, const float* z, int SB,
     q.out = c->netbuf.as<float>();
     int rc = run_query(c, q, mode, st);
     if (rc) return rc;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev2, st));
     CUDA_TRY(launch_composite(rays, z, q.out, n_rays, K, white, rgb, depth, weights, st));
     g_launches++;
+    if (c->timing) {
+        CUDA_TRY(cudaEventRecord(c->ev3, st));
+        CUDA_TRY(cudaEventSynchronize(c->ev3));
+        CUDA_TRY(cudaEventElapsedTime(&c->last_composite_ms, c->ev2, c->ev3));
+    }
     return DINER_OK;
 }
 
@@ -309,6 +326,7 @@ extern "C" int diner_composite(diner_ctx* c, const float* rays, const float* z, 
     int rc = check_ready(c);
     if (rc) return rc;
     if ((rc = check_render_args(c, SB, NR, K, -1, -1))) return rc;
+    if ((long long)SB * NR == 0) return DINER_OK;
     if (!rays || !z || !rgb || !depth) return fail(DINER_E_INVALID, "NULL pointer argument");
     CUDA_TRY(cudaSetDevice(c->device));
     const long long l0 = g_launches;
@@ -323,6 +341,7 @@ extern "C" int diner_render(diner_ctx* c, const float* rays, int SB, int NR, int
     int rc = check_ready(c);
     if (rc) return rc;
     if ((rc = check_render_args(c, SB, NR, K, C, G))) return rc;
+    if ((long long)SB * NR == 0) return DINER_OK;
     if (!rays || !rgb || !depth) return fail(DINER_E_INVALID, "NULL pointer argument");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -376,10 +395,30 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     return DINER_OK;
 }
 
+extern "C" int diner_debug_sync(diner_ctx* c) {
+    if (!c) return fail(DINER_E_INVALID, "ctx is NULL");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess)
+        return fail(DINER_E_CUDA, "device sync: %s (tcgen05 watchdog code %d: 10 producer/empty, 20 mma/operand, 30-31 mma/weights, 4x-5x worker/accumulator, 90 smem misaligned)",
+                    cudaGetErrorString(e), c->tc.err_flag ? *c->tc.err_flag : -1);
+    return DINER_OK;
+}
+
 extern "C" long long diner_launch_count(diner_ctx* c) { return c ? c->launches : 0; }
 extern "C" int diner_set_timing(diner_ctx* c, int enabled) {
     if (!c) return fail(DINER_E_INVALID, "ctx is NULL");
     c->timing = enabled;
+    c->tc.timing = enabled != 0;
     return DINER_OK;
 }
 extern "C" float diner_last_mlp_ms(diner_ctx* c) { return c ? c->last_mlp_ms : 0.f; }
+extern "C" float diner_last_stage_ms(diner_ctx* c, int stage) {
+    if (!c) return 0.f;
+    switch (stage) {
+        case 0: return c->last_sampler_ms;
+        case 1: return c->tc.ms_pre;
+        case 2: return c->tc.ms_post;
+        case 3: return c->last_composite_ms;
+        default: return c->last_mlp_ms;
+    }
+}

@@ -35,7 +35,9 @@ constexpr int HID = 512;                    // d_hidden served by this path
 constexpr int MT = HID / 128;               // M-tiles
 constexpr int KBLK = 64;                    // K elements per weight tile (one 128-byte swizzle atom)
 constexpr int WTILE_BYTES = 128 * KBLK * 2; // 16 KiB
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 512;                // 16 warps: 1 MMA issuer, 8 workers, 7 weight producers
+constexpr int NUM_PRODUCERS = 7;               // bulk-TMA ops of one warp are serialised (~0.4 us each, measured):
+                                               // bandwidth scales with the number of issuing warps
 constexpr int WORKER_WARP0 = 4;
 constexpr int NUM_WORKER_WARPS = 8;
 constexpr int NUM_WORKERS = NUM_WORKER_WARPS * 32;
@@ -109,6 +111,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
             __trap();
         }
     }
+}
+// one lane of a converged warp (the instruction operands of UTCHMMA / UBLKCP live in uniform registers: issuing them from
+// inside a lane-divergent branch makes the compiler emit a uniformisation loop per instruction, ~100 cycles each)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    return leader != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -297,26 +306,55 @@ template <bool PARITY>
 __device__ __forceinline__ void gather_latent(const Args& a, int wwarp, int lane, uint8_t* Bhi, uint8_t* Blo,
                                               const RowTap* taps) {
     const SceneDev& s = a.s;
-    const int n_cg = s.L >> 5;
-    const int n_tasks = 8 * n_cg;
+    const int n_cp = s.L >> 6;                 // pairs of 32-channel groups
+    const int n_tasks = 8 * n_cp;
 #pragma unroll 1
     for (int t = wwarp; t < n_tasks; t += NUM_WORKER_WARPS) {
-        const int rg = t / n_cg, cg = t % n_cg;
-        const int k = 32 * cg + lane;
-        float acc[8];
+        const int rg = t / n_cp, cp = t % n_cp;
+        const int k = 64 * cp + lane;
+        float acc0[8], acc1[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const RowTap rt = taps[8 * rg + i];
             const float* b00 = s.latent + (size_t)rt.pix00 * s.L + k;
             const size_t ox = (rt.dxy & 1) ? (size_t)s.L : 0, oy = (rt.dxy & 2) ? (size_t)s.Wl * s.L : 0;
             const float v00 = __ldg(b00), v01 = __ldg(b00 + ox), v10 = __ldg(b00 + oy), v11 = __ldg(b00 + oy + ox);
-            acc[i] = v00 * (rt.ex * rt.ey) + v01 * (rt.wx * rt.ey) + v10 * (rt.ex * rt.wy) + v11 * (rt.wx * rt.wy);
+            const float u00 = __ldg(b00 + 32), u01 = __ldg(b00 + ox + 32), u10 = __ldg(b00 + oy + 32), u11 = __ldg(b00 + oy + ox + 32);
+            const float w00 = rt.ex * rt.ey, w01 = rt.wx * rt.ey, w10 = rt.ex * rt.wy, w11 = rt.wx * rt.wy;
+            acc0[i] = v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11;
+            acc1[i] = u00 * w00 + u01 * w01 + u10 * w10 + u11 * w11;
         }
         uint4 hi, lo;
-        split8(acc, hi, lo);
-        const uint32_t off = b_off(k, rg);
+        split8(acc0, hi, lo);
+        uint32_t off = b_off(k, rg);
         *(uint4*)(Bhi + off) = hi;
         if (PARITY) *(uint4*)(Blo + off) = lo;
+        split8(acc1, hi, lo);
+        off = b_off(k + 32, rg);
+        *(uint4*)(Bhi + off) = hi;
+        if (PARITY) *(uint4*)(Blo + off) = lo;
+    }
+}
+
+// mean over the NV adjacent columns of each sample (resnetfc.py:148-151); NV is a compile-time constant so that
+// the 32 accumulator registers are indexed statically (dynamic indexing would spill them to local memory)
+template <int NV>
+__device__ __forceinline__ void combine_store(const uint32_t* v, float bv, float* dst) {
+    constexpr int PER = 32 / NV;
+    float o[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        float acc = __uint_as_float(v[j * NV]);
+#pragma unroll
+        for (int vv = 1; vv < NV; ++vv) acc += __uint_as_float(v[j * NV + vv]);
+        o[j] = acc * (1.0f / (float)NV) + bv;
+    }
+    if constexpr (PER >= 4) {
+#pragma unroll
+        for (int j = 0; j < PER; j += 4) *(float4*)(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) dst[j] = o[j];
     }
 }
 
@@ -378,26 +416,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_tc_kernel(const __grid_con
     const long long first = (long long)blockIdx.x, stride = (long long)gridDim.x;
     const long long n_rounds = (a.n_tiles + stride - 1) / stride;
 
-    if (warp == 0) {
-        // ===== weight producer: 1-D bulk TMA of 16 KiB tiles, each CTA of the cluster multicasts 1/CL of every tile
-        if (lane == 0) {
-            uint32_t use = 0;
+    const int prod_idx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : (warp >= 12 ? warp - 9 : -1)));
+    if (prod_idx >= 0) {
+        // ===== weight producers: 1-D bulk TMA of 16 KiB tiles.  Ring stage st is always filled by producer
+        //       st % NUM_PRODUCERS, so every barrier sees its uses in order from one thread (a parity wait cannot
+        //       tell "one phase ahead" from "two phases ahead").  Each CTA of a cluster multicasts 1/CL of a tile.
+        {
             constexpr uint32_t SLICE = WTILE_BYTES / CL;
-            for (long long rd = 0; rd < n_rounds; ++rd) {
-                for (int t = 0; t < a.tiles_per_layerset; ++t, ++use) {
-                    const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
+            const bool leader = elect_one();
+            const long long total_uses = n_rounds * a.tiles_per_layerset;
+            for (long long base = 0; base < total_uses; base += C::NST) {
+                for (int st = prod_idx; st < C::NST; st += NUM_PRODUCERS) {
+                    const long long use = base + st;
+                    if (use >= total_uses) break;
+                    const int t = (int)(use % a.tiles_per_layerset);
+                    const uint32_t ph = (uint32_t)((use / C::NST) & 1);
                     mbar_wait(bar_empty + 8 * st, ph ^ 1, a.err, 10);
-                    mbar_arrive_expect_tx(bar_full + 8 * st, WTILE_BYTES);
-                    const size_t gt = PARITY ? (size_t)t : (size_t)2 * t;          // fast mode skips the lo tiles
-                    bulk_g2s<CL>(smem_base + st * WTILE_BYTES + crank * SLICE, a.wstream + gt * WTILE_BYTES + crank * SLICE,
-                                 SLICE, bar_full + 8 * st);
+                    if (leader) {
+                        mbar_arrive_expect_tx(bar_full + 8 * st, WTILE_BYTES);
+                        const size_t gt = PARITY ? (size_t)t : (size_t)2 * t;      // fast mode skips the lo tiles
+                        bulk_g2s<CL>(smem_base + st * WTILE_BYTES + crank * SLICE, a.wstream + gt * WTILE_BYTES + crank * SLICE,
+                                     SLICE, bar_full + 8 * st);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread)
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow, one elected lane issues
+        {
             constexpr uint32_t IDESC = make_idesc(128, TILE_N);
+            const bool leader = elect_one();
             const uint64_t bdesc_hi = make_desc(smem_base + C::OFF_B_HI, 0, 1024);
             const uint64_t bdesc_lo = make_desc(smem_base + C::OFF_B_LO, 0, 1024);
             uint32_t use = 0, it = 0;
@@ -413,36 +462,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_tc_kernel(const __grid_con
                                 const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
                                 mbar_wait(bar_full + 8 * st, ph, a.err, 30);
                                 tc_fence_after();
-                                const uint64_t adesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
+                                if (leader) {
+                                    const uint64_t adesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint64_t bo = (uint64_t)(((kb * 4 + j) * 2048) >> 4);
-                                    umma_bf16(d, adesc + 2 * j, bdesc_hi + bo, IDESC, (gs.accumulate | kb | j) ? 1u : 0u);
-                                    if (PARITY) umma_bf16(d, adesc + 2 * j, bdesc_lo + bo, IDESC, 1u);
+                                    for (int j = 0; j < 4; ++j) {
+                                        const uint64_t bo = (uint64_t)(((kb * 4 + j) * 2048) >> 4);
+                                        umma_bf16(d, adesc + 2 * j, bdesc_hi + bo, IDESC, (gs.accumulate | kb | j) ? 1u : 0u);
+                                        if (PARITY) umma_bf16(d, adesc + 2 * j, bdesc_lo + bo, IDESC, 1u);
+                                    }
+                                    umma_commit_stage<CL>(bar_empty + 8 * st);
                                 }
-                                umma_commit_stage<CL>(bar_empty + 8 * st);
+                                __syncwarp();
                                 ++use;
                             }
                             if (PARITY) {   // lo weight tile: lo*hi
                                 const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
                                 mbar_wait(bar_full + 8 * st, ph, a.err, 31);
                                 tc_fence_after();
-                                const uint64_t adesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
+                                if (leader) {
+                                    const uint64_t adesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint64_t bo = (uint64_t)(((kb * 4 + j) * 2048) >> 4);
-                                    umma_bf16(d, adesc + 2 * j, bdesc_hi + bo, IDESC, 1u);
+                                    for (int j = 0; j < 4; ++j) {
+                                        const uint64_t bo = (uint64_t)(((kb * 4 + j) * 2048) >> 4);
+                                        umma_bf16(d, adesc + 2 * j, bdesc_hi + bo, IDESC, 1u);
+                                    }
+                                    umma_commit_stage<CL>(bar_empty + 8 * st);
                                 }
-                                umma_commit_stage<CL>(bar_empty + 8 * st);
+                                __syncwarp();
                                 ++use;
                             }
                         }
                     }
-                    umma_commit_local(bar_acc);
+                    if (leader) umma_commit_local(bar_acc);
+                    __syncwarp();
                 }
             }
         }
-    } else if (warp >= WORKER_WARP0) {
+    } else if (warp >= WORKER_WARP0 && warp < WORKER_WARP0 + NUM_WORKER_WARPS) {
         // ===== workers: operand producers + epilogues.  TMEM lane quarter q = warp % 4, column half hf
         const int wwarp = warp - WORKER_WARP0, wt = threadIdx.x - WORKER_WARP0 * 32;
         const int q = warp & 3, hf = wwarp >> 2;
@@ -476,7 +532,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_tc_kernel(const __grid_con
                 const int per = 32 / a.NV;                                       // samples in this thread's 32 columns
                 const long long tileB = tile / a.NV;
                 const int n0 = (int)(tile % a.NV) * a.spv + hf * per;
-                const float inv = 1.0f / (float)a.NV;
 #pragma unroll 1
                 for (int m = 0; m < MT; ++m) {
                     uint32_t v[32];
@@ -485,10 +540,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_tc_kernel(const __grid_con
                     const float bv = __ldg(cb + h);
                     if (live) {
                         float* dst = a.xc + ((size_t)tileB * HID + h) * TILE_N + n0;
-                        for (int j = 0; j < per; ++j) {
-                            float acc = __uint_as_float(v[j * a.NV]);
-                            for (int vv = 1; vv < a.NV; ++vv) acc += __uint_as_float(v[j * a.NV + vv]);
-                            dst[j] = acc * inv + bv;
+                        switch (a.NV) {
+                            case 1: combine_store<1>(v, bv, dst); break;
+                            case 2: combine_store<2>(v, bv, dst); break;
+                            case 4: combine_store<4>(v, bv, dst); break;
+                            case 8: combine_store<8>(v, bv, dst); break;
+                            case 16: combine_store<16>(v, bv, dst); break;
+                            default: combine_store<32>(v, bv, dst); break;
                         }
                     }
                 }
@@ -618,7 +676,8 @@ void tc_release(TcState& t) {
     if (t.wpack) cudaFree(t.wpack);
     if (t.bias) cudaFree(t.bias);
     if (t.scratch) cudaFree(t.scratch);
-    if (t.err_flag) cudaFree(t.err_flag);
+    if (t.err_flag) cudaFreeHost(t.err_flag);
+    for (int i = 0; i < 4; ++i) if (t.ev[i]) { cudaEventDestroy(t.ev[i]); t.ev[i] = nullptr; }
     t.wpack = nullptr; t.bias = nullptr; t.scratch = nullptr; t.err_flag = nullptr;
     t.wpack_bytes = t.scratch_bytes = 0;
     t.ready = false;
@@ -646,7 +705,10 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
         t.wpack_bytes = bytes;
     }
     if (!t.bias) TCK(cudaMalloc((void**)&t.bias, (size_t)(4 * DINER_MAX_BLOCKS + 4) * HID * sizeof(float)));
-    if (!t.err_flag) { TCK(cudaMalloc((void**)&t.err_flag, sizeof(int))); TCK(cudaMemsetAsync(t.err_flag, 0, sizeof(int), st)); }
+    if (!t.err_flag) {   // host-mapped so the watchdog code survives a trapped kernel
+        TCK(cudaHostAlloc((void**)&t.err_flag, sizeof(int), cudaHostAllocMapped));
+        *t.err_flag = 0;
+    }
     uint8_t* p = (uint8_t*)t.wpack;
     auto pack = [&](const float* W, int out_dim, int in_dim, int nkb, int n_mt) -> cudaError_t {
         pack_weight_kernel<<<n_mt * nkb, 256, 0, st>>>(W, out_dim, in_dim, nkb, p);
@@ -791,6 +853,8 @@ cudaError_t tc_query(TcState& t, const SceneDev& s, const MlpDev& m, const Query
     pre.out = post.out = q.out;
     pre.err = post.err = t.err_flag;
     pre.n_total = post.n_total = total;
+    t.ms_pre = t.ms_post = 0.f;
+    if (t.timing && !t.ev[0]) for (int i = 0; i < 4; ++i) TCK(cudaEventCreate(&t.ev[i]));
     for (long long s0 = 0; s0 < total; s0 += sub) {
         const long long ns = total - s0 < sub ? total - s0 : sub;
         pre.s_begin = post.s_begin = s0;
@@ -799,12 +863,19 @@ cudaError_t tc_query(TcState& t, const SceneDev& s, const MlpDev& m, const Query
         post.n_tiles = (ns + TILE_N - 1) / TILE_N;
         long long g1 = ((pre.n_tiles + cl - 1) / cl) * cl, g2 = ((post.n_tiles + cl - 1) / cl) * cl;
         const int grid1 = (int)(g1 < grid_cap ? g1 : grid_cap), grid2 = (int)(g2 < grid_cap ? g2 : grid_cap);
-        if (parity) {
-            TCK((launch_cl<true, false>(pre, grid1, cl, st)));
-            TCK((launch_cl<true, true>(post, grid2, cl, st)));
-        } else {
-            TCK((launch_cl<false, false>(pre, grid1, cl, st)));
-            TCK((launch_cl<false, true>(post, grid2, cl, st)));
+        if (t.timing) TCK(cudaEventRecord(t.ev[0], st));
+        if (parity) TCK((launch_cl<true, false>(pre, grid1, cl, st)));
+        else TCK((launch_cl<false, false>(pre, grid1, cl, st)));
+        if (t.timing) TCK(cudaEventRecord(t.ev[1], st));
+        if (parity) TCK((launch_cl<true, true>(post, grid2, cl, st)));
+        else TCK((launch_cl<false, true>(post, grid2, cl, st)));
+        if (t.timing) {
+            TCK(cudaEventRecord(t.ev[2], st));
+            TCK(cudaEventSynchronize(t.ev[2]));
+            float a = 0.f, b = 0.f;
+            TCK(cudaEventElapsedTime(&a, t.ev[0], t.ev[1]));
+            TCK(cudaEventElapsedTime(&b, t.ev[1], t.ev[2]));
+            t.ms_pre += a; t.ms_post += b;
         }
     }
     return cudaSuccess;

@@ -17,7 +17,10 @@ struct TcState {
     size_t bias_post_off = 0;
     int cluster = 1;              // thread-block cluster size for weight multicast (1, 2 or 4)
     long long sub_batch = 0;      // samples per PRE/POST launch pair (0 = default)
-    int max_grid[3] = {0, 0, 0};  // co-resident CTAs for cluster sizes 1, 2, 4 (queried lazily)
+    int max_grid[3] = {0, 0, 0};
+    bool timing = false;          // per-kernel CUDA-event timing (adds one sync per sub-batch)
+    float ms_pre = 0.f, ms_post = 0.f;   // accumulated over the last tc_query call
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // co-resident CTAs for cluster sizes 1, 2, 4 (queried lazily)
 };
 
 cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st);

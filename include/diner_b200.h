@@ -111,12 +111,18 @@ int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, i
  * weight multicast: 1, 2 or 4) or "sub_batch" (samples per PRE/POST launch pair). */
 int diner_set_option(diner_ctx* ctx, const char* key, long long value);
 
+/* cudaDeviceSynchronize + decoded tcgen05 watchdog code on failure (debugging aid). */
+int diner_debug_sync(diner_ctx* ctx);
+
 /* Number of kernels this library launched on behalf of ctx since creation (bench.py's gpu_launches). */
 long long diner_launch_count(diner_ctx* ctx);
 /* Device time in ms of the MLP kernels of the last render/composite/query call when timing was
  * enabled with diner_set_timing(ctx, 1) (CUDA events on the caller's stream; forces a sync). */
 int diner_set_timing(diner_ctx* ctx, int enabled);
 float diner_last_mlp_ms(diner_ctx* ctx);
+/* Per-stage device time of the last call (timing enabled): 0 sampler, 1 MLP PRE kernel(s) (per sample-view layers),
+ * 2 MLP POST kernel(s) (per sample layers), 3 compositing. */
+float diner_last_stage_ms(diner_ctx* ctx, int stage);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ with torch.no_grad():
     model = product_model(batch, latent, mlp, "cuda", mode)
     t0 = time.time()
     out1 = model(pts, vd)
-    torch.cuda.synchronize()
+    model.context().debug_sync()
     t1 = time.time()
     w1, rgb1, d1 = rend.composite(model, rays, z)
     torch.cuda.synchronize()
