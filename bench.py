@@ -92,7 +92,7 @@ def build_inputs():
     return batch, latent, mlp, rays
 
 
-def cpu_baseline(batch, latent, mlp, rays, n_rays=1536, warm=256):
+def cpu_baseline(batch, latent, mlp, rays, n_rays=12288, warm=256):
     """The oracle port (torch-CPU restatement pinned to the reference) on this box's host cores, bounded sample."""
     from oracle import diner_oracle as O
     from diner_b200 import synthetic as S
@@ -118,7 +118,7 @@ def reference_arm(args):
     if rank != 0:
         return
     batch, latent, mlp, rays = build_inputs()
-    n_rays = 1024
+    n_rays = 4096
     vals = []
     for i in range(args.warmup + args.steps):
         cb = cpu_baseline(batch, latent, mlp, rays, n_rays=n_rays, warm=64 if i == 0 else 8)
@@ -167,20 +167,18 @@ def main():
     n_total = H * W
     per = (n_total + world - 1) // world
     lo, hi = rank * per, min(n_total, (rank + 1) * per)
-    rays_host = rays[:, lo:hi].contiguous().pin_memory()
+    from diner_b200.multi_gpu import render_sharded
+    rays_host = rays.contiguous().pin_memory()          # every rank holds the ray list; it renders rays[lo:hi]
     rays_dev = rays_host.to(dev)
-    gathered = torch.empty(world, per, 4, device=dev) if world > 1 else None
-    mine = torch.zeros(per, 4, device=dev)
     ctx = model.context()
 
-    def step(src):
+    def local_render(r):
         with torch.no_grad():
-            out = rend(model, src)
-        if world > 1:                                   # one all-gather of rgb|depth per image
-            mine[:hi - lo, :3] = out.fine.rgb[0]
-            mine[:hi - lo, 3] = out.fine.depth[0]
-            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
-        return out
+            o = rend(model, r)
+        return o.fine.rgb, o.fine.depth
+
+    def step(src):
+        return render_sharded(local_render, src)        # one NCCL all-gather of rgb|depth per image when world > 1
 
     def sync():
         if world > 1:
@@ -203,14 +201,14 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
     # end-to-end: pinned host rays in, rgb + depth back on the host, every step
-    rgb_h = torch.empty(1, hi - lo, 3).pin_memory()
-    dep_h = torch.empty(1, hi - lo).pin_memory()
+    rgb_h = torch.empty(1, n_total, 3).pin_memory()
+    dep_h = torch.empty(1, n_total).pin_memory()
     sync()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = step(rays_host.to(dev, non_blocking=True))
-        rgb_h.copy_(out.fine.rgb, non_blocking=True)
-        dep_h.copy_(out.fine.depth, non_blocking=True)
+        rgb_d, dep_d = step(rays_host.to(dev, non_blocking=True))
+        rgb_h.copy_(rgb_d, non_blocking=True)
+        dep_h.copy_(dep_d, non_blocking=True)
         torch.cuda.synchronize()
     sync()
     ms_e2e = (time.perf_counter() - t0) * 1e3
@@ -250,7 +248,7 @@ def main():
                        "l2": "inputs larger than L2 (839 MB fp32 latent, 537 MB activations scratch per 524288 samples)",
                        "cluster": int(os.environ.get("DINER_TC_CLUSTER", "1"))},
             "e2e": {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
-                    "h2d_bytes_per_step": rays_host.numel() * 4 * world, "d2h_bytes_per_step": (rgb_h.numel() + dep_h.numel()) * 4 * world},
+                    "h2d_bytes_per_step": rays_host.numel() * 4, "d2h_bytes_per_step": (rgb_h.numel() + dep_h.numel()) * 4},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "tc::mlp_tc_kernel<PRE> (per sample-view ResnetFC layers)",
