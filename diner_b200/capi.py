@@ -98,7 +98,7 @@ class Context:
         self._check(self.lib.diner_create(ctypes.byref(h), idx))
         self.handle = h
         self._keep = []
-        for key, env in (("cluster", "DINER_TC_CLUSTER"), ("sub_batch", "DINER_TC_SUB_BATCH")):
+        for key, env in (("cluster", "DINER_TC_CLUSTER"), ("sub_batch", "DINER_TC_SUB_BATCH"), ("kernel", "DINER_TC_KERNEL")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))
 

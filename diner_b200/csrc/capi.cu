@@ -223,7 +223,9 @@ static int run_query(diner_ctx* c, const QueryArgs& q, int mode, cudaStream_t st
     } else if (mode == DINER_MODE_PARITY || mode == DINER_MODE_FAST) {
         if (!c->tc.ready)
             return fail(DINER_E_UNSUPPORTED, "tensor-core path unavailable for this MLP shape: %s", c->tc.why);
-        cudaError_t e = tc_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st);
+        cudaError_t e = (c->tc.kernel == 2 && (c->scene.L % 256) == 0)
+                            ? tc2_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st)
+                            : tc_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st);
         if (e == cudaErrorNotSupported) return fail(DINER_E_UNSUPPORTED, "tensor-core path: %s", c->tc.why);
         if (e != cudaSuccess) return fail(DINER_E_CUDA, "tc_query: %s (watchdog code %d)", cudaGetErrorString(e), c->tc.err_flag ? *c->tc.err_flag : -1);
     } else {
@@ -386,6 +388,9 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     if (!strcmp(key, "cluster")) {
         if (value != 1 && value != 2 && value != 4) return fail(DINER_E_INVALID, "cluster must be 1, 2 or 4");
         c->tc.cluster = (int)value;
+    } else if (!strcmp(key, "kernel")) {
+        if (value != 1 && value != 2) return fail(DINER_E_INVALID, "kernel must be 1 (single-CTA) or 2 (CTA pair)");
+        c->tc.kernel = (int)value;
     } else if (!strcmp(key, "sub_batch")) {
         if (value < 64) return fail(DINER_E_INVALID, "sub_batch must be >= 64");
         c->tc.sub_batch = value;

@@ -4,4 +4,5 @@
 #include "mlp_simt.cu"
 #include "composite.cu"
 #include "mlp_tc.cu"
+#include "mlp_tc2.cu"
 #include "capi.cu"

@@ -27,6 +27,9 @@
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
+
+#define TCK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) return _e; } while (0)
 
 namespace tc {
 
@@ -677,13 +680,13 @@ void tc_release(TcState& t) {
     if (t.bias) cudaFree(t.bias);
     if (t.scratch) cudaFree(t.scratch);
     if (t.err_flag) cudaFreeHost(t.err_flag);
+    if (t.table2) cudaFree(t.table2);
+    t.table2 = nullptr; t.table2_parity = -1;
     for (int i = 0; i < 4; ++i) if (t.ev[i]) { cudaEventDestroy(t.ev[i]); t.ev[i] = nullptr; }
     t.wpack = nullptr; t.bias = nullptr; t.scratch = nullptr; t.err_flag = nullptr;
     t.wpack_bytes = t.scratch_bytes = 0;
     t.ready = false;
 }
-
-#define TCK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) return _e; } while (0)
 
 cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
     using namespace tc;
@@ -696,7 +699,8 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
     const int kbz = m.d_latent / KBLK, kbh = HID / KBLK;
     t.n_pre = n_pre; t.n_post = n_post;
     t.pairs_pre = MT * 1 + n_pre * (MT * kbz + 2 * MT * kbh);
-    t.pairs_post = n_post * 2 * MT * kbh + kbh;
+    t.pairs_post = n_post * 2 * MT * kbh + 2 * kbh;       // lin_out packed as 2 M-tiles (the second is zeros, for the pair kernel)
+    t.pairs_post_v1 = t.pairs_post - kbh;
     const size_t bytes = (size_t)(t.pairs_pre + t.pairs_post) * 2 * WTILE_BYTES;
     if (bytes > t.wpack_bytes) {
         if (t.wpack) cudaFree(t.wpack);
@@ -726,7 +730,7 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
         TCK(pack(m.w_fc0[b], HID, HID, kbh, MT));
         TCK(pack(m.w_fc1[b], HID, HID, kbh, MT));
     }
-    TCK(pack(m.w_out, m.d_out, HID, kbh, 1));
+    TCK(pack(m.w_out, m.d_out, HID, kbh, 2));
     t.bias_post_off = (size_t)(2 * DINER_MAX_BLOCKS + 2) * HID;
     pack_bias_kernel<<<(HID + 127) / 128, 128, 0, st>>>(m, t.bias, t.bias + t.bias_post_off);
     g_launches++;
@@ -846,7 +850,7 @@ cudaError_t tc_query(TcState& t, const SceneDev& s, const MlpDev& m, const Query
     post.steps[n++] = GemmStep{(short)kbh, 1, COL_NET, 0};
     post.n_steps = n;
     pre.tiles_per_layerset = t.pairs_pre * (parity ? 2 : 1);
-    post.tiles_per_layerset = t.pairs_post * (parity ? 2 : 1);
+    post.tiles_per_layerset = t.pairs_post_v1 * (parity ? 2 : 1);
     pre.NV = post.NV = NV;
     pre.spv = post.spv = TILE_N / NV;
     pre.xc = post.xc = (float*)t.scratch;

@@ -18,6 +18,10 @@ struct TcState {
     int cluster = 1;              // thread-block cluster size for weight multicast (1, 2 or 4)
     long long sub_batch = 0;      // samples per PRE/POST launch pair (0 = default)
     int max_grid[3] = {0, 0, 0};
+    int kernel = 2;               // 1 = single-CTA transposed kernel (mlp_tc.cu), 2 = CTA-pair kernel (mlp_tc2.cu)
+    int pairs_post_v1 = 0;        // POST tile pairs the v1 kernel consumes (the pair kernel's zero lin_out tile excluded)
+    int* table2 = nullptr;        // pair kernel: per-rank weight tile tables
+    int table2_parity = -1, uses2_pre = 0, uses2_post = 0, max_grid2 = 0;
     bool timing = false;          // per-kernel CUDA-event timing (adds one sync per sub-batch)
     float ms_pre = 0.f, ms_post = 0.f;   // accumulated over the last tc_query call
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // co-resident CTAs for cluster sizes 1, 2, 4 (queried lazily)
@@ -27,3 +31,5 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st);
 cudaError_t tc_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity,
                      int num_sms, cudaStream_t st);
 void tc_release(TcState& t);
+cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity,
+                      int num_sms, cudaStream_t st);

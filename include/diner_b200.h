@@ -108,7 +108,8 @@ int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, i
                     int mode, float* rgb, float* depth, float* weights, void* stream);
 
 /* Tuning knobs of the tcgen05 path (not part of the reference API): key = "cluster" (thread-block cluster size for
- * weight multicast: 1, 2 or 4) or "sub_batch" (samples per PRE/POST launch pair). */
+ * weight multicast of kernel 1: 1, 2 or 4), "kernel" (1 = single-CTA tcgen05 kernel, 2 = CTA-pair cta_group::2 kernel, default)
+ * or "sub_batch" (samples per PRE/POST launch pair). */
 int diner_set_option(diner_ctx* ctx, const char* key, long long value);
 
 /* cudaDeviceSynchronize + decoded tcgen05 watchdog code on failure (debugging aid). */
