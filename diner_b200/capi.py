@@ -98,7 +98,8 @@ class Context:
         self._check(self.lib.diner_create(ctypes.byref(h), idx))
         self.handle = h
         self._keep = []
-        for key, env in (("cluster", "DINER_TC_CLUSTER"), ("sub_batch", "DINER_TC_SUB_BATCH"), ("kernel", "DINER_TC_KERNEL")):
+        for key, env in (("cluster", "DINER_TC_CLUSTER"), ("sub_batch", "DINER_TC_SUB_BATCH"), ("kernel", "DINER_TC_KERNEL"),
+                         ("dbg_skip", "DINER_TC_DBG_SKIP")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))
 

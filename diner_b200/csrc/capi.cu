@@ -391,6 +391,8 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     } else if (!strcmp(key, "kernel")) {
         if (value != 1 && value != 2) return fail(DINER_E_INVALID, "kernel must be 1 (single-CTA) or 2 (CTA pair)");
         c->tc.kernel = (int)value;
+    } else if (!strcmp(key, "dbg_skip")) {
+        c->tc.dbg_skip = (int)value;
     } else if (!strcmp(key, "sub_batch")) {
         if (value < 64) return fail(DINER_E_INVALID, "sub_batch must be >= 64");
         c->tc.sub_batch = value;

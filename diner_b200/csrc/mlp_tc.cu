@@ -735,6 +735,25 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
     pack_bias_kernel<<<(HID + 127) / 128, 128, 0, st>>>(m, t.bias, t.bias + t.bias_post_off);
     g_launches++;
     TCK(cudaGetLastError());
+    {   // tensor map over the packed stream for the pair kernel's cta_group::2 TMA loads (plain linear 16 KiB boxes)
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        t.wmap_ok = false;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
+            cuuint64_t gdim[2] = {64, (cuuint64_t)(t.pairs_pre + t.pairs_post) * 2 * 128};
+            cuuint64_t gstr[1] = {128};
+            cuuint32_t box[2] = {64, 128};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = ((EncodeFn)fn)(&t.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t.wpack, gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            t.wmap_ok = (r == CUDA_SUCCESS);
+        }
+        (void)cudaGetLastError();
+    }
     t.ready = true;
     t.why[0] = 0;
     return cudaSuccess;

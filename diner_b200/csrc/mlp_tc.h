@@ -1,5 +1,6 @@
 // tcgen05 (5th-gen tensor core) path of the per-sample network: packed weights + launch entry points.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "diner_internal.h"
 
@@ -22,6 +23,9 @@ struct TcState {
     int pairs_post_v1 = 0;        // POST tile pairs the v1 kernel consumes (the pair kernel's zero lin_out tile excluded)
     int* table2 = nullptr;        // pair kernel: per-rank weight tile tables
     int table2_parity = -1, uses2_pre = 0, uses2_post = 0, max_grid2 = 0;
+    CUtensorMap wmap;             // 2-D view of wpack: rows of 128 B, box = one 16 KiB tile (pair kernel: cta_group::2 TMA)
+    bool wmap_ok = false;
+    int dbg_skip = 0;             // profiling experiments (pair kernel PRE): see tc2::Args::dbg_skip
     bool timing = false;          // per-kernel CUDA-event timing (adds one sync per sub-batch)
     float ms_pre = 0.f, ms_post = 0.f;   // accumulated over the last tc_query call
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // co-resident CTAs for cluster sizes 1, 2, 4 (queried lazily)

@@ -45,10 +45,12 @@ constexpr int WTILE_BYTES = 128 * KBLK * 2; // 16 KiB: 128 hidden rows x 64 k, K
 constexpr int ACT_KB_BYTES = ROWS * 128;    // 8 KiB per 64-wide K block of the activation operand
 constexpr int ACT_BYTES = ACT_KB_BYTES * (HID / KBLK);   // 64 KiB per bf16 copy
 constexpr int NUM_THREADS = 512;
-constexpr int NUM_PRODUCERS = 7;
+constexpr int NUM_PRODUCERS = 3;               // warps 0,2,3: each CTA streams only half of every weight tile (~33 B/clk needed)
 constexpr int WORKER_WARP0 = 4;
 constexpr int NUM_WORKER_WARPS = 8;
 constexpr int NUM_WORKERS = NUM_WORKER_WARPS * 32;
+constexpr int NUM_HELPER_WARPS = 4;             // warps 12..15: extra hands for the operand-producing phases (prep, gather); no TMEM access
+constexpr int NUM_OPND_WARPS = NUM_WORKER_WARPS + NUM_HELPER_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_X = 0, COL_NET = 256;
 constexpr int MAX_STEPS = 3 * DINER_MAX_BLOCKS + 2;
@@ -62,6 +64,7 @@ struct GemmStep {
 };
 
 struct Args {
+    CUtensorMap wmap;           // packed weight stream as rows of 128 B; one box = one 16 KiB tile
     SceneDev s;
     QueryArgs q;
     const uint8_t* wstream;     // packed weight tiles (16 KiB units), shared with mlp_tc.cu's packing
@@ -74,6 +77,7 @@ struct Args {
     float* xc;                  // [sample][512] fp32 view-combined activations (sub-batch relative)
     float* out;
     int* err;
+    int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
 };
 
 // ---- cluster / pair PTX ------------------------------------------------------------------------
@@ -156,7 +160,8 @@ __device__ __forceinline__ void epilogue_to_A(uint32_t tmem, int colbase, const 
 template <bool PARITY>
 __device__ __forceinline__ void prep_rows(const Args& a, long long tile, int wt, uint8_t* Ahi, uint8_t* Alo, RowTap* taps) {
     const SceneDev& s = a.s;
-    const int r = wt & 63, part = wt >> 6;
+    const int r = wt & 63, part = wt >> 6;            // NUM_OPND_WARPS * 32 / 64 threads per row
+    constexpr int PARTS = NUM_OPND_WARPS * 32 / 64;
     long long smp = a.s_begin + tile * a.spv + r / a.NV;
     if (smp >= a.n_total) smp = a.n_total - 1;
     const int v = r % a.NV;
@@ -190,7 +195,7 @@ __device__ __forceinline__ void prep_rows(const Args& a, long long tile, int wt,
     }
     const int d_in = 3 + 6 * s.num_freqs + 3 + 1 + 2 * s.num_freqs;
 #pragma unroll 1
-    for (int e = part; e < KBLK; e += 4) {
+    for (int e = part; e < KBLK; e += PARTS) {
         const float val = e < d_in ? feature_elem(e, s.num_freqs, s.freqs, xc, yc, zc, dxc, dyc, dzc, dd) : 0.0f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(val);
         const uint32_t off = act_off(r, e >> 3) + (uint32_t)(e & 7) * 2u;
@@ -205,31 +210,29 @@ template <bool PARITY>
 __device__ __forceinline__ void gather_latent(const Args& a, int wwarp, int lane, uint8_t* Ahi, uint8_t* Alo, const RowTap* taps) {
     const SceneDev& s = a.s;
     const int passes = s.L >> 8;
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        const int r = wwarp * 8 + i;
+    const int n_units = ROWS * passes;
+#pragma unroll 2
+    for (int u = wwarp; u < n_units; u += NUM_OPND_WARPS) {
+        const int r = u / passes, p = u % passes;
         const RowTap rt = taps[r];
         const size_t ox = (rt.dxy & 1) ? (size_t)s.L : 0, oy = (rt.dxy & 2) ? (size_t)s.Wl * s.L : 0;
         const float w00 = rt.ex * rt.ey, w01 = rt.wx * rt.ey, w10 = rt.ex * rt.wy, w11 = rt.wx * rt.wy;
-#pragma unroll 2
-        for (int p = 0; p < passes; ++p) {
-            const int k0 = 256 * p + 8 * lane;
-            const float* b00 = s.latent + (size_t)rt.pix00 * s.L + k0;
-            const float4 a0 = __ldg((const float4*)b00), a1 = __ldg((const float4*)(b00 + 4));
-            const float4 b0 = __ldg((const float4*)(b00 + ox)), b1 = __ldg((const float4*)(b00 + ox + 4));
-            const float4 c0 = __ldg((const float4*)(b00 + oy)), c1 = __ldg((const float4*)(b00 + oy + 4));
-            const float4 d0 = __ldg((const float4*)(b00 + oy + ox)), d1 = __ldg((const float4*)(b00 + oy + ox + 4));
-            float x[8];
-            x[0] = a0.x * w00 + b0.x * w01 + c0.x * w10 + d0.x * w11; x[1] = a0.y * w00 + b0.y * w01 + c0.y * w10 + d0.y * w11;
-            x[2] = a0.z * w00 + b0.z * w01 + c0.z * w10 + d0.z * w11; x[3] = a0.w * w00 + b0.w * w01 + c0.w * w10 + d0.w * w11;
-            x[4] = a1.x * w00 + b1.x * w01 + c1.x * w10 + d1.x * w11; x[5] = a1.y * w00 + b1.y * w01 + c1.y * w10 + d1.y * w11;
-            x[6] = a1.z * w00 + b1.z * w01 + c1.z * w10 + d1.z * w11; x[7] = a1.w * w00 + b1.w * w01 + c1.w * w10 + d1.w * w11;
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const uint32_t off = act_off(r, k0 >> 3);
-            *(uint4*)(Ahi + off) = hi;
-            if (PARITY) *(uint4*)(Alo + off) = lo;
-        }
+        const int k0 = 256 * p + 8 * lane;
+        const float* b00 = s.latent + (size_t)rt.pix00 * s.L + k0;
+        const float4 a0 = __ldg((const float4*)b00), a1 = __ldg((const float4*)(b00 + 4));
+        const float4 b0 = __ldg((const float4*)(b00 + ox)), b1 = __ldg((const float4*)(b00 + ox + 4));
+        const float4 c0 = __ldg((const float4*)(b00 + oy)), c1 = __ldg((const float4*)(b00 + oy + 4));
+        const float4 d0 = __ldg((const float4*)(b00 + oy + ox)), d1 = __ldg((const float4*)(b00 + oy + ox + 4));
+        float x[8];
+        x[0] = a0.x * w00 + b0.x * w01 + c0.x * w10 + d0.x * w11; x[1] = a0.y * w00 + b0.y * w01 + c0.y * w10 + d0.y * w11;
+        x[2] = a0.z * w00 + b0.z * w01 + c0.z * w10 + d0.z * w11; x[3] = a0.w * w00 + b0.w * w01 + c0.w * w10 + d0.w * w11;
+        x[4] = a1.x * w00 + b1.x * w01 + c1.x * w10 + d1.x * w11; x[5] = a1.y * w00 + b1.y * w01 + c1.y * w10 + d1.y * w11;
+        x[6] = a1.z * w00 + b1.z * w01 + c1.z * w10 + d1.z * w11; x[7] = a1.w * w00 + b1.w * w01 + c1.w * w10 + d1.w * w11;
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = act_off(r, k0 >> 3);
+        *(uint4*)(Ahi + off) = hi;
+        if (PARITY) *(uint4*)(Alo + off) = lo;
     }
 }
 
@@ -263,7 +266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 90); __trap(); }
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); mbar_init(bar_pfull + 8 * i, 1); }
-        mbar_init(bar_opnd, 2 * NUM_WORKER_WARPS);
+        mbar_init(bar_opnd, 2 * NUM_OPND_WARPS);
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
@@ -283,11 +286,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     const long long n_rounds = (a.n_tiles + stride - 1) / stride;
     const long long total_uses = n_rounds * a.uses_per_tile;
 
-    const int prod_idx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : (warp >= 12 ? warp - 9 : -1)));
+    const int prod_idx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
     if (prod_idx >= 0) {
-        // ===== weight producers (this CTA's half of every weight tile); stage st is always filled by producer st % NUM_PRODUCERS
+        // ===== weight producers (this CTA's half of every weight tile); stage st is always filled by producer st % NUM_PRODUCERS.
+        //       2-SM TMA: both CTAs' copies complete_tx on the LEADER's full barrier, so the MMA issuer needs no software relay.
         const bool leader = elect_one();
         const int* table = a.tile_table + (size_t)crank * a.uses_per_tile;
+        const uint32_t leader_full = map_to_cta(bar_full, 0);
         for (long long base = 0; base < total_uses; base += C::NST) {
             for (int st = prod_idx; st < C::NST; st += NUM_PRODUCERS) {
                 const long long use = base + st;
@@ -296,23 +301,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 const uint32_t ph = (uint32_t)((use / C::NST) & 1);
                 mbar_wait(bar_empty + 8 * st, ph ^ 1, a.err, 10);
                 if (leader) {
-                    mbar_arrive_expect_tx(bar_full + 8 * st, WTILE_BYTES);
-                    tc::bulk_g2s<1>(smem_base + st * WTILE_BYTES, a.wstream + (size_t)__ldg(table + t) * WTILE_BYTES, WTILE_BYTES, bar_full + 8 * st);
+                    if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, 2 * WTILE_BYTES);
+                    const int row = __ldg(table + t) * 128;
+                    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(smem_base + st * WTILE_BYTES), "l"(&a.wmap), "r"(0), "r"(row), "r"(leader_full + 8 * st) : "memory");
                 }
                 __syncwarp();
             }
         }
-    } else if (warp == 1 && !is_leader_cta) {
-        // ===== peer CTA: relay "my half of the stage has landed" to the leader's barrier
-        const bool leader = elect_one();
-        const uint32_t remote_pfull = map_to_cta(bar_pfull, 0);
-        for (long long use = 0; use < total_uses; ++use) {
-            const uint32_t st = (uint32_t)(use % C::NST), ph = (uint32_t)((use / C::NST) & 1);
-            mbar_wait(bar_full + 8 * st, ph, a.err, 32);
-            if (leader) mbar_arrive_remote(remote_pfull + 8 * st);
-            __syncwarp();
-        }
-    } else if (warp == 1) {
+    } else if (warp == 1 && is_leader_cta) {
         // ===== leader CTA: MMA issuer for the pair (converged warp, one elected lane)
         const bool leader = elect_one();
         uint32_t use = 0, it = 0;
@@ -328,14 +325,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         {   // W_hi tile: A_hi*W_hi (+ A_lo*W_hi)
                             const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
                             mbar_wait(bar_full + 8 * st, ph, a.err, 30);
-                            mbar_wait(bar_pfull + 8 * st, ph, a.err, 33);
                             tc_fence_after();
                             if (leader) {
                                 const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
                                 const uint64_t ahi = make_desc(smem_base + C::OFF_A_HI + kb * ACT_KB_BYTES, 16, 1024);
                                 const uint64_t alo = make_desc(smem_base + C::OFF_A_LO + kb * ACT_KB_BYTES, 16, 1024);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
+                                for (int j = 0; j < ((a.dbg_skip & 8) ? 0 : 4); ++j) {
                                     umma2_bf16(d, ahi + 2 * j, bdesc + 2 * j, idesc, (gs.accumulate | kb | j) ? 1u : 0u);
                                     if (PARITY) umma2_bf16(d, alo + 2 * j, bdesc + 2 * j, idesc, 1u);
                                 }
@@ -347,13 +343,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         if (PARITY) {   // W_lo tile: A_hi*W_lo
                             const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
                             mbar_wait(bar_full + 8 * st, ph, a.err, 31);
-                            mbar_wait(bar_pfull + 8 * st, ph, a.err, 34);
                             tc_fence_after();
                             if (leader) {
                                 const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
                                 const uint64_t ahi = make_desc(smem_base + C::OFF_A_HI + kb * ACT_KB_BYTES, 16, 1024);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) umma2_bf16(d, ahi + 2 * j, bdesc + 2 * j, idesc, 1u);
+                                for (int j = 0; j < ((a.dbg_skip & 8) ? 0 : 4); ++j) umma2_bf16(d, ahi + 2 * j, bdesc + 2 * j, idesc, 1u);
                                 umma2_commit_pair(bar_empty + 8 * st);
                             }
                             __syncwarp();
@@ -365,10 +360,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 __syncwarp();
             }
         }
-    } else if (warp >= WORKER_WARP0 && warp < WORKER_WARP0 + NUM_WORKER_WARPS) {
-        // ===== workers.  TMEM lanes 32q..32q+31: row = 32*(q&1)+lane, hidden half (q>>1) of this warp's N tile n2
+    } else if (warp >= WORKER_WARP0) {
+        // ===== workers (warps 4..11) + helpers (warps 12..15; prep and gather only).
+        //       worker TMEM lanes 32q..32q+31: row = 32*(q&1)+lane, hidden half (q>>1) of this warp's N tile n2
         const int wwarp = warp - WORKER_WARP0, wt = threadIdx.x - WORKER_WARP0 * 32;
-        const int q = warp & 3, n2 = wwarp >> 2;
+        const bool helper = wwarp >= NUM_WORKER_WARPS;
+        const int q = warp & 3, n2 = (wwarp >> 2) & 1;
         const int r = 32 * (q & 1) + lane;
         uint32_t it = 0;
         for (long long rd = 0; rd < n_rounds; ++rd) {
@@ -376,20 +373,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             const bool live = tile_raw < a.n_tiles;
             const long long tile = live ? tile_raw : a.n_tiles - 1;
             if constexpr (!POST) {
-                prep_rows<PARITY>(a, tile, wt, Ahi, Alo, taps);
+                if (!(a.dbg_skip & 4)) prep_rows<PARITY>(a, tile, wt, Ahi, Alo, taps);
                 worker_arrive(leader_opnd, lane);                                // -> lin_in
                 for (int b = 0; b < a.n_blocks; ++b) {
                     mbar_wait(bar_acc, it & 1, a.err, 40); ++it;
                     tc_fence_after();
-                    gather_latent<PARITY>(a, wwarp, lane, Ahi, Alo, taps);
+                    if (!(a.dbg_skip & 1)) gather_latent<PARITY>(a, wwarp, lane, Ahi, Alo, taps);
                     worker_arrive(leader_opnd, lane);                            // -> lin_z[b]
                     mbar_wait(bar_acc, it & 1, a.err, 41); ++it;
                     tc_fence_after();
-                    epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2);
+                    if (!helper && !(a.dbg_skip & 2)) epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2);
                     worker_arrive(leader_opnd, lane);                            // -> fc_0[b]
                     mbar_wait(bar_acc, it & 1, a.err, 42); ++it;
                     tc_fence_after();
-                    epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + b) * HID, Ahi, Alo, q, lane, n2);
+                    if (!helper && !(a.dbg_skip & 2)) epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + b) * HID, Ahi, Alo, q, lane, n2);
                     worker_arrive(leader_opnd, lane);                            // -> fc_1[b]
                 }
                 mbar_wait(bar_acc, it & 1, a.err, 43); ++it;
@@ -399,7 +396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 const float inv = 1.0f / (float)a.NV;
                 const long long smp = tile * a.spv + r / a.NV;                   // sample within the sub-batch
 #pragma unroll 1
-                for (int c32 = 0; c32 < 4; ++c32) {
+                for (int c32 = 0; c32 < (helper ? 0 : 4); ++c32) {
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
                     const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
@@ -423,7 +420,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 long long smp = tile * ROWS + r;
                 if (smp >= a.n_samples) smp = a.n_samples - 1;
 #pragma unroll 1
-                for (int c32 = 0; c32 < 4; ++c32) {
+                for (int c32 = 0; c32 < (helper ? 0 : 4); ++c32) {
                     const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
                     const float4* src = (const float4*)(a.xc + (size_t)smp * HID + h0);
                     uint32_t v[32];
@@ -450,16 +447,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 for (int b = 0; b < a.n_blocks; ++b) {
                     mbar_wait(bar_acc, it & 1, a.err, 50); ++it;
                     tc_fence_after();
-                    epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + 1 + b) * HID, Ahi, Alo, q, lane, n2);
+                    if (!helper) epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + 1 + b) * HID, Ahi, Alo, q, lane, n2);
                     worker_arrive(leader_opnd, lane);                            // -> fc_1[b]
                     mbar_wait(bar_acc, it & 1, a.err, 51); ++it;
                     tc_fence_after();
-                    epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)(b + 1) * HID, Ahi, Alo, q, lane, n2);
+                    if (!helper) epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)(b + 1) * HID, Ahi, Alo, q, lane, n2);
                     worker_arrive(leader_opnd, lane);                            // -> next fc_0 / lin_out
                 }
                 mbar_wait(bar_acc, it & 1, a.err, 52); ++it;                     // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
                 tc_fence_after();
-                if (q < 2 && n2 == 0) {
+                if (!helper && q < 2 && n2 == 0) {
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)COL_NET, v);
                     const long long s_loc = tile * ROWS + r;
@@ -472,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     }
                 }
                 tc_fence_before();
-                asm volatile("bar.sync 1, %0;" ::"n"(NUM_WORKERS) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
             }
         }
     }
@@ -564,6 +561,8 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         t.scratch_bytes = need;
     }
     Args pre{}, post{};
+    if (!t.wmap_ok) { snprintf(t.why, sizeof(t.why), "cuTensorMapEncodeTiled unavailable"); return cudaErrorNotSupported; }
+    pre.wmap = post.wmap = t.wmap;
     pre.s = s; pre.q = q; post.s = s; post.q = q;
     pre.wstream = post.wstream = (const uint8_t*)t.wpack;
     pre.tile_table = t.table2; post.tile_table = t.table2 + 2 * t.uses2_pre;
@@ -591,6 +590,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.out = post.out = q.out;
     pre.err = post.err = t.err_flag;
     pre.n_total = post.n_total = total;
+    pre.dbg_skip = t.dbg_skip; post.dbg_skip = 0;
     t.ms_pre = t.ms_post = 0.f;
     if (t.timing && !t.ev[0]) for (int i = 0; i < 4; ++i) TCK(cudaEventCreate(&t.ev[i]));
     for (long long s0 = 0; s0 < total; s0 += sub) {
