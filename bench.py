@@ -113,6 +113,33 @@ def cpu_baseline(batch, latent, mlp, rays, n_rays=12288, warm=256):
                 sample="%d rays of the 512x512 workload (strided), oracle/diner_oracle.py on torch-CPU fp32, %.1f s" % (n_rays, dt))
 
 
+def gpu_eager_baseline(batch, latent, mlp, rays, dev, n_rays=4096):
+    """The reference algorithm as eager PyTorch ON THE GPU (oracle port moved to cuda): the stand-in for the
+    reference's own CUDA execution (SURVEY §8(d) 'GPU reference baseline'), one ray batch of 4096 = diner.py:57."""
+    from oracle import diner_oracle as O
+    from diner_b200 import synthetic as S
+    scene = O.make_scene_state(batch, latent, mlp)               # built on the host, then moved
+    for f in ("poses", "focal", "c", "image_shape", "latent", "depths", "depths_std", "normals"):
+        setattr(scene, f, getattr(scene, f).to(dev))
+    scene.mlp = {k: v.to(dev) for k, v in mlp.items()}
+    start = (H // 2) * W - n_rays // 2
+    r = rays[:, start:start + n_rays].contiguous().to(dev)
+    noise = [S.hash_uniform((1, n_rays, C), 1, 1).to(dev), S.hash_normal((1, n_rays, G), 1, 2).to(dev), S.hash_uniform((1, n_rays, K), 1, 3).to(dev)]
+    with torch.no_grad():
+        for _ in range(2):
+            O.render(scene, r, K, C, G, WHITE, *noise)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            O.render(scene, r, K, C, G, WHITE, *noise)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return dict(value=n_rays / (ms * 1e-3), unit="rays/s", kind="reference algorithm as eager fp32 PyTorch on this GPU (oracle port on cuda)",
+                sample="%d-ray batch (image centre), %.1f ms" % (n_rays, ms))
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -261,6 +288,12 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(batch, latent, mlp, rays)
+            try:
+                del model
+                torch.cuda.empty_cache()
+                line["gpu_eager_baseline"] = gpu_eager_baseline(batch, latent, mlp, rays, dev)
+            except Exception as e:      # reported extra, never allowed to break the contract line
+                line["gpu_eager_baseline"] = {"unavailable": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -25,6 +25,7 @@ using tc::smem_u32;
 using tc::mbar_init;
 using tc::mbar_arrive_expect_tx;
 using tc::mbar_wait;
+using tc::mbar_poll;
 using tc::fence_barrier_init;
 using tc::fence_proxy_async;
 using tc::tc_fence_before;
@@ -33,6 +34,8 @@ using tc::elect_one;
 using tc::cluster_ctarank;
 using tc::cluster_sync_all;
 using tc::tmem_ld32;
+using tc::tmem_ld32_issue;
+using tc::tmem_ld_wait;
 using tc::tmem_st32;
 using tc::make_desc;
 using tc::split8;
@@ -77,6 +80,7 @@ struct Args {
     float* xc;                  // [sample][512] fp32 view-combined activations (sub-batch relative)
     float* out;
     int* err;
+    long long* dbg_ts;          // profiling: clock64 stamps of pair 0 in round 1 ([cta][role][slot])
     int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
 };
 
@@ -130,30 +134,43 @@ template <bool PARITY> struct Cfg {
 
 // ---- worker building blocks ----------------------------------------------------------------------
 // TMEM region (this warp's N tile: 128 columns) + per-column bias -> relu -> bf16 hi/lo chunks of the A operand
+// 32 accumulator columns of row r (hidden h0..h0+31) + bias -> relu -> four 16-byte K-major chunks (hi / lo)
+template <bool PARITY>
+__device__ __forceinline__ void convert32(const uint32_t* v, const float* __restrict__ bias, int h0, int r, uint8_t* Ahi, uint8_t* Alo) {
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+        const float4 b0 = __ldg((const float4*)(bias + h0 + 8 * c8)), b1 = __ldg((const float4*)(bias + h0 + 8 * c8 + 4));
+        float x[8];
+        x[0] = fmaxf(__uint_as_float(v[8 * c8 + 0]) + b0.x, 0.0f); x[1] = fmaxf(__uint_as_float(v[8 * c8 + 1]) + b0.y, 0.0f);
+        x[2] = fmaxf(__uint_as_float(v[8 * c8 + 2]) + b0.z, 0.0f); x[3] = fmaxf(__uint_as_float(v[8 * c8 + 3]) + b0.w, 0.0f);
+        x[4] = fmaxf(__uint_as_float(v[8 * c8 + 4]) + b1.x, 0.0f); x[5] = fmaxf(__uint_as_float(v[8 * c8 + 5]) + b1.y, 0.0f);
+        x[6] = fmaxf(__uint_as_float(v[8 * c8 + 6]) + b1.z, 0.0f); x[7] = fmaxf(__uint_as_float(v[8 * c8 + 7]) + b1.w, 0.0f);
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = act_off(r, (h0 >> 3) + c8);
+        *(uint4*)(Ahi + off) = hi;
+        if (PARITY) *(uint4*)(Alo + off) = lo;
+    }
+}
+// TMEM region (this warp's N tile: 128 columns) + per-column bias -> relu -> bf16 hi/lo chunks of the A operand.
+// Two TMEM loads are kept in flight (the second 64 columns load while the first are converted).
 template <bool PARITY>
 __device__ __forceinline__ void epilogue_to_A(uint32_t tmem, int colbase, const float* __restrict__ bias, uint8_t* Ahi,
                                               uint8_t* Alo, int q, int lane, int n2) {
     const int r = 32 * (q & 1) + lane;
-#pragma unroll 1
-    for (int c32 = 0; c32 < 4; ++c32) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(colbase + 128 * n2 + 32 * c32), v);
-        const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-            const float4 b0 = __ldg((const float4*)(bias + h0 + 8 * c8)), b1 = __ldg((const float4*)(bias + h0 + 8 * c8 + 4));
-            float x[8];
-            x[0] = fmaxf(__uint_as_float(v[8 * c8 + 0]) + b0.x, 0.0f); x[1] = fmaxf(__uint_as_float(v[8 * c8 + 1]) + b0.y, 0.0f);
-            x[2] = fmaxf(__uint_as_float(v[8 * c8 + 2]) + b0.z, 0.0f); x[3] = fmaxf(__uint_as_float(v[8 * c8 + 3]) + b0.w, 0.0f);
-            x[4] = fmaxf(__uint_as_float(v[8 * c8 + 4]) + b1.x, 0.0f); x[5] = fmaxf(__uint_as_float(v[8 * c8 + 5]) + b1.y, 0.0f);
-            x[6] = fmaxf(__uint_as_float(v[8 * c8 + 6]) + b1.z, 0.0f); x[7] = fmaxf(__uint_as_float(v[8 * c8 + 7]) + b1.w, 0.0f);
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const uint32_t off = act_off(r, (h0 >> 3) + c8);
-            *(uint4*)(Ahi + off) = hi;
-            if (PARITY) *(uint4*)(Alo + off) = lo;
-        }
-    }
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(colbase + 128 * n2);
+    const int hb = 256 * n2 + 128 * (q >> 1);
+    uint32_t va[32], vb[32];
+    tmem_ld32_issue(t0, va);
+    tmem_ld32_issue(t0 + 32, vb);
+    tmem_ld_wait();
+    convert32<PARITY>(va, bias, hb, r, Ahi, Alo);
+    tmem_ld32_issue(t0 + 64, va);
+    convert32<PARITY>(vb, bias, hb + 32, r, Ahi, Alo);
+    tmem_ld32_issue(t0 + 96, vb);
+    tmem_ld_wait();
+    convert32<PARITY>(va, bias, hb + 64, r, Ahi, Alo);
+    convert32<PARITY>(vb, bias, hb + 96, r, Ahi, Alo);
 }
 
 // PRE prep: 4 threads per row -> lin_in A operand (K block 0) + bilinear tap set
@@ -210,40 +227,103 @@ template <bool PARITY>
 __device__ __forceinline__ void gather_latent(const Args& a, int wwarp, int lane, uint8_t* Ahi, uint8_t* Alo, const RowTap* taps) {
     const SceneDev& s = a.s;
     const int passes = s.L >> 8;
-    const int n_units = ROWS * passes;
-#pragma unroll 2
-    for (int u = wwarp; u < n_units; u += NUM_OPND_WARPS) {
+    const int n_units = ROWS * passes;              // unit = (row, 256-channel pass); lane = 8 channels
+    auto issue = [&](int u, float4 (&f)[8], float (&w)[4], uint32_t& off) {
         const int r = u / passes, p = u % passes;
         const RowTap rt = taps[r];
         const size_t ox = (rt.dxy & 1) ? (size_t)s.L : 0, oy = (rt.dxy & 2) ? (size_t)s.Wl * s.L : 0;
-        const float w00 = rt.ex * rt.ey, w01 = rt.wx * rt.ey, w10 = rt.ex * rt.wy, w11 = rt.wx * rt.wy;
+        w[0] = rt.ex * rt.ey; w[1] = rt.wx * rt.ey; w[2] = rt.ex * rt.wy; w[3] = rt.wx * rt.wy;
         const int k0 = 256 * p + 8 * lane;
         const float* b00 = s.latent + (size_t)rt.pix00 * s.L + k0;
-        const float4 a0 = __ldg((const float4*)b00), a1 = __ldg((const float4*)(b00 + 4));
-        const float4 b0 = __ldg((const float4*)(b00 + ox)), b1 = __ldg((const float4*)(b00 + ox + 4));
-        const float4 c0 = __ldg((const float4*)(b00 + oy)), c1 = __ldg((const float4*)(b00 + oy + 4));
-        const float4 d0 = __ldg((const float4*)(b00 + oy + ox)), d1 = __ldg((const float4*)(b00 + oy + ox + 4));
+        f[0] = __ldg((const float4*)b00); f[1] = __ldg((const float4*)(b00 + 4));
+        f[2] = __ldg((const float4*)(b00 + ox)); f[3] = __ldg((const float4*)(b00 + ox + 4));
+        f[4] = __ldg((const float4*)(b00 + oy)); f[5] = __ldg((const float4*)(b00 + oy + 4));
+        f[6] = __ldg((const float4*)(b00 + oy + ox)); f[7] = __ldg((const float4*)(b00 + oy + ox + 4));
+        off = act_off(r, k0 >> 3);
+    };
+    auto finish = [&](const float4 (&f)[8], const float (&w)[4], uint32_t off) {
         float x[8];
-        x[0] = a0.x * w00 + b0.x * w01 + c0.x * w10 + d0.x * w11; x[1] = a0.y * w00 + b0.y * w01 + c0.y * w10 + d0.y * w11;
-        x[2] = a0.z * w00 + b0.z * w01 + c0.z * w10 + d0.z * w11; x[3] = a0.w * w00 + b0.w * w01 + c0.w * w10 + d0.w * w11;
-        x[4] = a1.x * w00 + b1.x * w01 + c1.x * w10 + d1.x * w11; x[5] = a1.y * w00 + b1.y * w01 + c1.y * w10 + d1.y * w11;
-        x[6] = a1.z * w00 + b1.z * w01 + c1.z * w10 + d1.z * w11; x[7] = a1.w * w00 + b1.w * w01 + c1.w * w10 + d1.w * w11;
+        x[0] = f[0].x * w[0] + f[2].x * w[1] + f[4].x * w[2] + f[6].x * w[3]; x[1] = f[0].y * w[0] + f[2].y * w[1] + f[4].y * w[2] + f[6].y * w[3];
+        x[2] = f[0].z * w[0] + f[2].z * w[1] + f[4].z * w[2] + f[6].z * w[3]; x[3] = f[0].w * w[0] + f[2].w * w[1] + f[4].w * w[2] + f[6].w * w[3];
+        x[4] = f[1].x * w[0] + f[3].x * w[1] + f[5].x * w[2] + f[7].x * w[3]; x[5] = f[1].y * w[0] + f[3].y * w[1] + f[5].y * w[2] + f[7].y * w[3];
+        x[6] = f[1].z * w[0] + f[3].z * w[1] + f[5].z * w[2] + f[7].z * w[3]; x[7] = f[1].w * w[0] + f[3].w * w[1] + f[5].w * w[2] + f[7].w * w[3];
         uint4 hi, lo;
         split8(x, hi, lo);
-        const uint32_t off = act_off(r, k0 >> 3);
         *(uint4*)(Ahi + off) = hi;
         if (PARITY) *(uint4*)(Alo + off) = lo;
+    };
+#pragma unroll 1
+    for (int u = wwarp; u < n_units; u += 2 * NUM_OPND_WARPS) {
+        float4 fa[8], fb[8];
+        float wa[4], wb[4];
+        uint32_t oa, ob = 0;
+        const bool two = u + NUM_OPND_WARPS < n_units;
+        issue(u, fa, wa, oa);
+        if (two) issue(u + NUM_OPND_WARPS, fb, wb, ob);
+        finish(fa, wa, oa);
+        if (two) finish(fb, wb, ob);
     }
 }
 
-// workers of BOTH CTAs arrive on the leader's operand barrier (count 16 warps)
-__device__ __forceinline__ void worker_arrive(uint32_t leader_bar, int lane) {
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_remote(leader_bar);
+// View-combine of 32 accumulator columns: reduce-scatter over the NV adjacent lanes (rows) of a sample.  After it, lane j of the
+// group holds 32/NV consecutive columns starting at the returned offset (summed over the NV views, pairwise order).
+template <int NV>
+__device__ __forceinline__ int combine_lanes(float (&v)[32], int lane) {
+    int cnt = 32, offset = 0;
+#pragma unroll
+    for (int m = NV / 2; m >= 1; m >>= 1) {
+        cnt >>= 1;
+        const bool upper = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < cnt) {
+                const float send = upper ? v[i] : v[cnt + i];
+                const float keep = upper ? v[cnt + i] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+        offset += upper ? cnt : 0;
+    }
+    return offset;
+}
+template <int NV>
+__device__ __forceinline__ void combine_store(uint32_t* raw, const float* __restrict__ cb, int h0, int lane, float* dst_sample, bool write) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+    const int off = combine_lanes<NV>(v, lane);
+    constexpr int CNT = 32 / NV;
+    if (write) {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) v[i] = v[i] * (1.0f / (float)NV) + __ldg(cb + h0 + off + i);
+        float* dst = dst_sample + h0 + off;
+        if constexpr (CNT >= 4) {
+#pragma unroll
+            for (int i = 0; i < CNT; i += 4) *(float4*)(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CNT; ++i) dst[i] = v[i];
+        }
+    }
 }
 
+// Operand hand-off to the MMA issuer (leader CTA).  Remote mbarrier arrives are slow (~1 us each and they serialise),
+// so the peer CTA first joins its 12 operand warps on a named barrier and sends ONE remote arrive; the leader's own
+// warps arrive locally.  Leader barrier count = NUM_OPND_WARPS + 1.
+__device__ __forceinline__ void worker_arrive(uint32_t bar_local, uint32_t bar_leader_remote, bool is_leader_cta, int wwarp, int lane) {
+    fence_proxy_async();
+    tc_fence_before();
+    if (is_leader_cta) {
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_local);
+    } else {
+        asm volatile("bar.sync 2, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+        if (wwarp == 0 && lane == 0) mbar_arrive_remote(bar_leader_remote);
+    }
+}
+
+#define TS(role, slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == 1 && lane == 0) a.dbg_ts[(blockIdx.x * 4 + (role)) * 64 + (slot)] = clock64(); } while (0)
+#define TSW() do { if (a.dbg_ts && blockIdx.x < 2 && rd == 1 && wwarp == 0 && lane == 0 && tsn < 64) a.dbg_ts[(blockIdx.x * 4 + 1) * 64 + tsn++] = clock64(); } while (0)
 // ---- the kernel ----------------------------------------------------------------------------------
 template <bool PARITY, bool POST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_pair_kernel(const __grid_constant__ Args a) {
@@ -266,7 +346,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 90); __trap(); }
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); mbar_init(bar_pfull + 8 * i, 1); }
-        mbar_init(bar_opnd, 2 * NUM_OPND_WARPS);
+        mbar_init(bar_opnd, NUM_OPND_WARPS + 1);
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
@@ -293,7 +373,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const bool leader = elect_one();
         const int* table = a.tile_table + (size_t)crank * a.uses_per_tile;
         const uint32_t leader_full = map_to_cta(bar_full, 0);
-        for (long long base = 0; base < total_uses; base += C::NST) {
+        for (long long base = 0; base < ((a.dbg_skip & 16) ? 0 : total_uses); base += C::NST) {
             for (int st = prod_idx; st < C::NST; st += NUM_PRODUCERS) {
                 const long long use = base + st;
                 if (use >= total_uses) break;
@@ -317,14 +397,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             for (int sidx = 0; sidx < a.n_steps; ++sidx, ++it) {
                 const GemmStep gs = a.steps[sidx];
                 const uint32_t idesc = make_idesc2(gs.n_width);
-                mbar_wait(bar_opnd, it & 1, a.err, 20);
+                if (a.dbg_skip & 64) mbar_poll(bar_opnd, it & 1, a.err, 20); else mbar_wait(bar_opnd, it & 1, a.err, 20);
                 tc_fence_after();
+                TS(0, 2 * sidx);
                 for (int n2 = 0; n2 < gs.n_tiles; ++n2) {
                     const uint32_t d = tmem + (uint32_t)(gs.dst_col + 128 * n2);
                     for (int kb = 0; kb < gs.nkb; ++kb) {
                         {   // W_hi tile: A_hi*W_hi (+ A_lo*W_hi)
                             const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
-                            mbar_wait(bar_full + 8 * st, ph, a.err, 30);
+                            if (!(a.dbg_skip & 16)) mbar_wait(bar_full + 8 * st, ph, a.err, 30);
                             tc_fence_after();
                             if (leader) {
                                 const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
@@ -335,14 +416,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                                     umma2_bf16(d, ahi + 2 * j, bdesc + 2 * j, idesc, (gs.accumulate | kb | j) ? 1u : 0u);
                                     if (PARITY) umma2_bf16(d, alo + 2 * j, bdesc + 2 * j, idesc, 1u);
                                 }
-                                umma2_commit_pair(bar_empty + 8 * st);
+                                if (!(a.dbg_skip & 16)) umma2_commit_pair(bar_empty + 8 * st);
                             }
                             __syncwarp();
                             ++use;
                         }
                         if (PARITY) {   // W_lo tile: A_hi*W_lo
                             const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
-                            mbar_wait(bar_full + 8 * st, ph, a.err, 31);
+                            if (!(a.dbg_skip & 16)) mbar_wait(bar_full + 8 * st, ph, a.err, 31);
                             tc_fence_after();
                             if (leader) {
                                 const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
@@ -356,8 +437,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         }
                     }
                 }
-                if (leader) umma2_commit_pair(bar_acc);
+                if (leader) {
+                    if (a.dbg_skip & 32) { tc::mbar_arrive(bar_acc); mbar_arrive_remote(map_to_cta(bar_acc, 1)); }   // experiment: software signal
+                    else umma2_commit_pair(bar_acc);
+                }
                 __syncwarp();
+                TS(0, 2 * sidx + 1);
             }
         }
     } else if (warp >= WORKER_WARP0) {
@@ -369,49 +454,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const int r = 32 * (q & 1) + lane;
         uint32_t it = 0;
         for (long long rd = 0; rd < n_rounds; ++rd) {
+            int tsn = 0; (void)tsn;
             const long long tile_raw = first + rd * stride;
             const bool live = tile_raw < a.n_tiles;
             const long long tile = live ? tile_raw : a.n_tiles - 1;
             if constexpr (!POST) {
                 if (!(a.dbg_skip & 4)) prep_rows<PARITY>(a, tile, wt, Ahi, Alo, taps);
-                worker_arrive(leader_opnd, lane);                                // -> lin_in
+                TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> lin_in
                 for (int b = 0; b < a.n_blocks; ++b) {
-                    mbar_wait(bar_acc, it & 1, a.err, 40); ++it;
+                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 40); else mbar_wait(bar_acc, it & 1, a.err, 40); ++it; TSW();
                     tc_fence_after();
                     if (!(a.dbg_skip & 1)) gather_latent<PARITY>(a, wwarp, lane, Ahi, Alo, taps);
-                    worker_arrive(leader_opnd, lane);                            // -> lin_z[b]
-                    mbar_wait(bar_acc, it & 1, a.err, 41); ++it;
+                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> lin_z[b]
+                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 41); else mbar_wait(bar_acc, it & 1, a.err, 41); ++it; TSW();
                     tc_fence_after();
                     if (!helper && !(a.dbg_skip & 2)) epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2);
-                    worker_arrive(leader_opnd, lane);                            // -> fc_0[b]
-                    mbar_wait(bar_acc, it & 1, a.err, 42); ++it;
+                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_0[b]
+                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 42); else mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
                     tc_fence_after();
                     if (!helper && !(a.dbg_skip & 2)) epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + b) * HID, Ahi, Alo, q, lane, n2);
-                    worker_arrive(leader_opnd, lane);                            // -> fc_1[b]
+                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b]
                 }
-                mbar_wait(bar_acc, it & 1, a.err, 43); ++it;
+                if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 43); else mbar_wait(bar_acc, it & 1, a.err, 43); ++it; TSW();
                 tc_fence_after();
                 // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
                 const float* cb = a.bias + (size_t)(2 * a.n_blocks) * HID;
-                const float inv = 1.0f / (float)a.NV;
                 const long long smp = tile * a.spv + r / a.NV;                   // sample within the sub-batch
+                const bool wr = live && smp < a.n_samples;
+                float* dst_sample = a.xc + (size_t)(wr ? smp : 0) * HID;
 #pragma unroll 1
-                for (int c32 = 0; c32 < (helper ? 0 : 4); ++c32) {
+                for (int c32 = 0; c32 < ((helper || (a.dbg_skip & 128)) ? 0 : 4); ++c32) {
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
                     const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
-                    float o[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = __uint_as_float(v[i]);
-                        float acc = x;
-                        for (int vv = 1; vv < a.NV; ++vv) acc += __shfl_down_sync(0xffffffffu, x, vv);
-                        o[i] = acc * inv + __ldg(cb + h0 + i);
-                    }
-                    if (live && (lane % a.NV) == 0 && smp < a.n_samples) {
-                        float4* dst = (float4*)(a.xc + (size_t)smp * HID + h0);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    switch (a.NV) {
+                        case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr); break;
+                        case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr); break;
+                        case 4: combine_store<4>(v, cb, h0, lane, dst_sample, wr); break;
+                        case 8: combine_store<8>(v, cb, h0, lane, dst_sample, wr); break;
+                        case 16: combine_store<16>(v, cb, h0, lane, dst_sample, wr); break;
+                        default: combine_store<32>(v, cb, h0, lane, dst_sample, wr); break;
                     }
                 }
                 tc_fence_before();
@@ -443,18 +525,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         if (PARITY) *(uint4*)(Alo + off) = lo;
                     }
                 }
-                worker_arrive(leader_opnd, lane);                                // -> fc_0 of the first post block
+                worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> fc_0 of the first post block
                 for (int b = 0; b < a.n_blocks; ++b) {
-                    mbar_wait(bar_acc, it & 1, a.err, 50); ++it;
+                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 50); else mbar_wait(bar_acc, it & 1, a.err, 50); ++it;
                     tc_fence_after();
                     if (!helper) epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + 1 + b) * HID, Ahi, Alo, q, lane, n2);
-                    worker_arrive(leader_opnd, lane);                            // -> fc_1[b]
-                    mbar_wait(bar_acc, it & 1, a.err, 51); ++it;
+                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b]
+                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 51); else mbar_wait(bar_acc, it & 1, a.err, 51); ++it;
                     tc_fence_after();
                     if (!helper) epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)(b + 1) * HID, Ahi, Alo, q, lane, n2);
-                    worker_arrive(leader_opnd, lane);                            // -> next fc_0 / lin_out
+                    worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> next fc_0 / lin_out
                 }
-                mbar_wait(bar_acc, it & 1, a.err, 52); ++it;                     // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
+                if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 52); else mbar_wait(bar_acc, it & 1, a.err, 52); ++it;                     // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
                 tc_fence_after();
                 if (!helper && q < 2 && n2 == 0) {
                     uint32_t v[32];
@@ -591,6 +673,9 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.err = post.err = t.err_flag;
     pre.n_total = post.n_total = total;
     pre.dbg_skip = t.dbg_skip; post.dbg_skip = 0;
+    static long long* dbg_ts = nullptr;
+    if ((t.dbg_skip & 512) && !dbg_ts) { TCK(cudaMallocManaged((void**)&dbg_ts, 8 * 64 * sizeof(long long))); memset(dbg_ts, 0, 8 * 64 * sizeof(long long)); }
+    pre.dbg_ts = (t.dbg_skip & 512) ? dbg_ts : nullptr; post.dbg_ts = nullptr;
     t.ms_pre = t.ms_post = 0.f;
     if (t.timing && !t.ev[0]) for (int i = 0; i < 4; ++i) TCK(cudaEventCreate(&t.ev[i]));
     for (long long s0 = 0; s0 < total; s0 += sub) {
@@ -612,6 +697,20 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
             TCK(cudaEventElapsedTime(&x, t.ev[0], t.ev[1]));
             TCK(cudaEventElapsedTime(&y, t.ev[1], t.ev[2]));
             t.ms_pre += x; t.ms_post += y;
+        }
+    }
+    if (pre.dbg_ts) {
+        TCK(cudaStreamSynchronize(st));
+        for (int cta = 0; cta < 2; ++cta) {
+            const long long t0 = pre.dbg_ts[(cta * 4 + 1) * 64];
+            fprintf(stderr, "[ts] cta %d worker stamps (arriving, woke, arriving, ...) cycles since first:", cta);
+            for (int i = 0; i < 22; ++i) fprintf(stderr, " %lld", pre.dbg_ts[(cta * 4 + 1) * 64 + i] - t0);
+            fprintf(stderr, "\n");
+            if (cta == 0) {
+                fprintf(stderr, "[ts] cta 0 mma stamps (opnd-ready, committed per step), same origin:");
+                for (int i = 0; i < 20; ++i) fprintf(stderr, " %lld", pre.dbg_ts[i] - t0);
+                fprintf(stderr, "\n");
+            }
         }
     }
     return cudaSuccess;

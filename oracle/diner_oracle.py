@@ -62,10 +62,10 @@ def positional_encoding(x, num_freqs=6, freq_factor=6.28):
     d = shp[-1]
     x2 = x.reshape(-1, d)
     freqs = freq_factor * 2.0 ** torch.arange(0, num_freqs)                      # :18
-    f = torch.repeat_interleave(freqs, 2).view(1, -1, 1).to(x2.dtype)             # :24-26
+    f = torch.repeat_interleave(freqs, 2).view(1, -1, 1).to(x2)                   # :24-26
     ph = torch.zeros(2 * num_freqs)
     ph[1::2] = np.pi * 0.5                                                        # :29-30
-    ph = ph.view(1, -1, 1).to(x2.dtype)
+    ph = ph.view(1, -1, 1).to(x2)
     e = x2.unsqueeze(1).repeat(1, 2 * num_freqs, 1)                               # :45
     e = torch.sin(torch.addcmul(ph, e, f)).view(x2.shape[0], -1)                  # :46-47
     e = torch.cat((x2, e), dim=-1)                                                # :49
@@ -97,7 +97,7 @@ def index_latent(scene: Scene, uv):
     """Bilinear / border gather of the latent with the feature-padding rescale (image_encoder.py:97-146)."""
     SB, NV, N, _ = uv.shape
     Hl, Wl = scene.latent.shape[-2:]
-    size = torch.tensor([Wl, Hl])
+    size = torch.tensor([Wl, Hl], device=uv.device)
     uv = uv * ((size - scene.feature_padding * 2) / size).view(1, 1, 1, 2)       # :113-114
     lat, g = _flat_grid(scene.latent, uv)
     s = F.grid_sample(lat, g, align_corners=False, mode="bilinear", padding_mode="border")
@@ -120,7 +120,7 @@ def exponential_padding(img, padding, double_width):
     """
     N, C, H, W = img.shape
     base = F.pad(img, [padding] * 4, mode="replicate")
-    ex = torch.zeros(N, C, H + 2 * padding, W + 2 * padding, dtype=img.dtype)
+    ex = torch.zeros(N, C, H + 2 * padding, W + 2 * padding, dtype=img.dtype, device=img.device)
     for i in range(padding):
         idx = padding - (i + 1)
         ex[:, :, idx, :] = i
@@ -136,7 +136,7 @@ def index_depth_std(scene: Scene, uv, pad_size=100, pad_double_width=12):
     SB, NV, N, _ = uv.shape
     d, g = _flat_grid(scene.depths_std, uv)
     H, W = d.shape[-2:]
-    img_size = torch.tensor([W, H], dtype=torch.float)
+    img_size = torch.tensor([W, H], dtype=torch.float, device=uv.device)
     padded = exponential_padding(d, pad_size, pad_double_width)
     g = g * (img_size / (img_size + 2 * pad_size)).view(1, 1, 1, 2)              # :157-158
     s = F.grid_sample(padded, g, mode="nearest", padding_mode="zeros", align_corners=False)
@@ -195,7 +195,7 @@ def sample_coarse(rays, C, u_coarse):
     r = rays.reshape(-1, 8)
     near, far = r[:, -2:-1], r[:, -1:]
     step = 1.0 / C
-    s = torch.linspace(0, 1 - step, C).unsqueeze(0).repeat(r.shape[0], 1)
+    s = torch.linspace(0, 1 - step, C, device=rays.device).unsqueeze(0).repeat(r.shape[0], 1)
     s = s + u_coarse.reshape(-1, C) * step
     return (near * (1 - s) + far * s).view(*shp[:-1], C)
 
@@ -243,7 +243,7 @@ def sample_depthguided(scene: Scene, rays, K, C, G, u_coarse, g_noise, return_au
         wn = w / w.sum(dim=-1, keepdims=True)                                      # torch_helpers.py:216
         mean = (x * wn).sum(dim=-1, keepdims=True)
         std = ((x - mean).pow(2) * wn).sum(dim=-1, keepdims=True).sqrt()
-        gs = torch.zeros(SB, NR, G)
+        gs = torch.zeros(SB, NR, G, device=rays.device)
         gs[ray_mask] = g_noise[ray_mask] * std + mean                              # :188
         z[..., -G:] = gs                                                           # :190
     if return_aux:

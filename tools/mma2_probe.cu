@@ -12,15 +12,17 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void cluster_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe2(int M, int N, int n_mma, long long* out) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe2(int M, int N, int n_mma, long long* out, int grp, int mcast) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t dummy[8];
     uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 64 * 1024 / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy[i])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -45,6 +47,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe2(int M
                 uint32_t acc = i > 0;
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                              ::"r"(tmem + (uint32_t)((i & 1) * 128)), "l"(ad + 2 * (i & 3)), "l"(bd + 2 * (i & 3)), "r"(idesc), "r"(acc) : "memory");
+                if (grp > 0 && (i & (grp - 1)) == grp - 1) {
+                    if (mcast) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&dummy[(i >> 2) & 7])), "h"((uint16_t)3) : "memory");
+                    else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy[(i >> 2) & 7])) : "memory");
+                }
             }
             __syncwarp();
         }
@@ -63,12 +69,11 @@ int main() {
     long long* out; CK(cudaMallocManaged(&out, 32));
     CK(cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     const int n = 4096;
-    struct { int M, N; } cfgs[] = {{128, 256}, {128, 128}, {128, 64}, {128, 32}, {256, 256}, {256, 128}, {256, 64}};
+    struct { int M, N, grp, mc; } cfgs[] = {{128, 256, 0, 0}, {128, 256, 8, 1}, {128, 256, 4, 1}, {128, 256, 4, 0}, {128, 256, 1, 1}, {128, 256, 1, 0}, {128, 64, 1, 1}, {128, 32, 1, 1}};
     for (auto c : cfgs) {
-        probe2<<<148, 128, 96 * 1024>>>(c.M, c.N, n, out);
+        probe2<<<148, 128, 96 * 1024>>>(c.M, c.N, n, out, c.grp, c.mc);
         CK(cudaDeviceSynchronize());
-        const double per_sm_macs = (double)(c.M / 2) * c.N * 16;
-        printf("cta_group::2  M=%3d N=%3d : %.1f cyc/MMA  -> %.0f MAC/clk/SM (peak 4096)\n", c.M, c.N, (double)out[0] / n, per_sm_macs / ((double)out[0] / n));
+        printf("cta_group::2  M=%3d N=%3d commit every %d MMAs (%s): %.1f cyc/MMA\n", c.M, c.N, c.grp, c.mc ? "multicast" : "local", (double)out[0] / n);
     }
     return 0;
 }
