@@ -166,3 +166,47 @@ def test_properties_and_edges():
         rend(model, rays[0])                      # reference asserts 3-D rays (nerf_renderer.py:412)
     with pytest.raises(RuntimeError):
         model.context().render(rays, 16, 200, 32, True, 0)   # n_gaussian > n_samples
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] at full size (512x512, 4 views, 64 samples/ray, 262 144 rays) through
+    size-independent properties: determinism, shard-vs-whole equality, white/black background relation,
+    weights in [0,1], and parity-mode vs fp32-mode agreement (1e-4) on a strided subset of the rays."""
+    import bench
+    batch, latent, mlp, rays = bench.build_inputs()
+    model = product_model(batch, latent, mlp, "cuda", "parity")
+    cfg = dict(K=bench.K, C=bench.C, G=bench.G, white=False)
+    rend = renderer_for(cfg)
+    rend.noise = dict(seed=1234)
+    rays = rays.cuda()
+    n = rays.shape[1]
+    with torch.no_grad():
+        full = rend(model, rays)
+        again = rend(model, rays)
+        assert torch.equal(full.fine.rgb, again.fine.rgb) and torch.equal(full.fine.depth, again.fine.depth)
+        assert bool(torch.isfinite(full.fine.rgb).all()) and bool(torch.isfinite(full.fine.depth).all())
+        # a strided subset rendered on its own, with the noise of the same logical rays, must reproduce the image
+        # (counter-based noise is keyed by ray index within the call, so compare through explicit sample depths)
+        ctx = model.context()
+        sub = torch.arange(0, n, 97, device="cuda")[:2048]
+        r_sub = rays[:, sub].contiguous()
+        z_sub = ctx.sample(r_sub, cfg["K"], cfg["C"], cfg["G"], dict(seed=7))
+        assert bool((z_sub[..., 1:] >= z_sub[..., :-1]).all())
+        w_p, rgb_p, d_p = ctx.composite(r_sub, z_sub, False, 1)
+        w_f, rgb_f, d_f = ctx.composite(r_sub, z_sub, False, 0)           # fp32 CUDA-core arithmetic
+        e = max(float((rgb_p - rgb_f).abs().max()), float((d_p - d_f).abs().max()))
+        print("full-size: parity vs fp32 on 2048 strided rays: max |err| %.3g" % e)
+        assert e <= TOL
+        assert float(w_p.min()) >= 0.0 and float(w_p.sum(-1).max()) <= 1.0 + 1e-5
+        w_w, rgb_w, _ = ctx.composite(r_sub, z_sub, True, 1)
+        assert (rgb_w - (rgb_p + 1 - w_p.sum(-1, keepdim=True))).abs().max() <= 2e-6
+        # two halves of the image == the whole image for the MLP + compositing stages (ray independence)
+        z_all = ctx.sample(rays, cfg["K"], cfg["C"], cfg["G"], dict(seed=7))
+        _, rgb_all, d_all = ctx.composite(rays, z_all, False, 1, want_weights=False)
+        h = n // 2
+        _, rgb_a, d_a = ctx.composite(rays[:, :h].contiguous(), z_all[:, :h].contiguous(), False, 1, want_weights=False)
+        _, rgb_b, d_b = ctx.composite(rays[:, h:].contiguous(), z_all[:, h:].contiguous(), False, 1, want_weights=False)
+        assert torch.equal(torch.cat((rgb_a, rgb_b), 1), rgb_all) and torch.equal(torch.cat((d_a, d_b), 1), d_all)
+        fg = float((full.fine.depth > 0).float().mean())
+        print("full-size: %.1f %% of rays hit geometry, rgb mean %.3f" % (100 * fg, float(full.fine.rgb.mean())))
+        assert fg > 0.05
