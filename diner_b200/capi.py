@@ -238,7 +238,7 @@ class Context:
 
     def last_stage_ms(self):
         """dict of device ms of the last call's stages (needs set_timing(True))."""
-        names = ("sampler", "mlp_pre", "mlp_post", "composite")
+        names = ("sampler", "mlp_pre", "mlp_post", "composite", "lin_z_maps")
         return {n: float(self.lib.diner_last_stage_ms(self.handle, i)) for i, n in enumerate(names)}
 
     def last_mlp_ms(self):

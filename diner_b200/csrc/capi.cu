@@ -189,6 +189,7 @@ extern "C" int diner_set_scene(diner_ctx* c, int SB, int NV, int L, int Hl, int 
     for (int i = 0; i < num_freqs; ++i) { s.freqs[i] = freq_factor * pw; pw *= 2.0f; }
     c->scene = s;
     c->has_scene = true;
+    c->tc.zmap_valid = false;        // hoisted lin_z maps are per scene
     return DINER_OK;
 }
 
@@ -223,7 +224,7 @@ static int run_query(diner_ctx* c, const QueryArgs& q, int mode, cudaStream_t st
     } else if (mode == DINER_MODE_PARITY || mode == DINER_MODE_FAST) {
         if (!c->tc.ready)
             return fail(DINER_E_UNSUPPORTED, "tensor-core path unavailable for this MLP shape: %s", c->tc.why);
-        cudaError_t e = (c->tc.kernel == 2 && (c->scene.L % 256) == 0)
+        cudaError_t e = (c->tc.kernel == 2 && (c->scene.L % 64) == 0 && c->scene.L <= 512)
                             ? tc2_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st)
                             : tc_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st);
         if (e == cudaErrorNotSupported) return fail(DINER_E_UNSUPPORTED, "tensor-core path: %s", c->tc.why);
@@ -391,6 +392,8 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     } else if (!strcmp(key, "kernel")) {
         if (value != 1 && value != 2) return fail(DINER_E_INVALID, "kernel must be 1 (single-CTA) or 2 (CTA pair)");
         c->tc.kernel = (int)value;
+    } else if (!strcmp(key, "rebuild_maps")) {
+        c->tc.zmap_valid = false;        // next query rebuilds the hoisted lin_z maps (bench: times the scene-prepare step)
     } else if (!strcmp(key, "dbg_skip")) {
         c->tc.dbg_skip = (int)value;
     } else if (!strcmp(key, "sub_batch")) {
@@ -426,6 +429,7 @@ extern "C" float diner_last_stage_ms(diner_ctx* c, int stage) {
         case 1: return c->tc.ms_pre;
         case 2: return c->tc.ms_post;
         case 3: return c->last_composite_ms;
+        case 4: return c->tc.ms_zmap;
         default: return c->last_mlp_ms;
     }
 }

@@ -207,6 +207,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st32_issue(uint32_t taddr, const uint32_t* v) {   // no wait: pair with tmem_st_wait()
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -710,6 +722,8 @@ void tc_release(TcState& t) {
     if (t.err_flag) cudaFreeHost(t.err_flag);
     if (t.table2) cudaFree(t.table2);
     t.table2 = nullptr; t.table2_parity = -1;
+    if (t.zmap) cudaFree(t.zmap);
+    t.zmap = nullptr; t.zmap_bytes = 0; t.zmap_valid = false;
     for (int i = 0; i < 4; ++i) if (t.ev[i]) { cudaEventDestroy(t.ev[i]); t.ev[i] = nullptr; }
     t.wpack = nullptr; t.bias = nullptr; t.scratch = nullptr; t.err_flag = nullptr;
     t.wpack_bytes = t.scratch_bytes = 0;
@@ -719,6 +733,8 @@ void tc_release(TcState& t) {
 cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
     using namespace tc;
     t.ready = false;
+    t.zmap_valid = false;         // the hoisted lin_z maps depend on the weights
+    t.table2_parity = -1;         // tile tables depend on the layer shapes
     const int n_pre = m.combine_layer < m.n_blocks ? m.combine_layer : m.n_blocks, n_post = m.n_blocks - n_pre;
     if (m.d_hidden != HID) { snprintf(t.why, sizeof(t.why), "d_hidden=%d (tcgen05 path serves 512)", m.d_hidden); return cudaSuccess; }
     if (m.d_in > KBLK) { snprintf(t.why, sizeof(t.why), "d_in=%d > 64", m.d_in); return cudaSuccess; }

@@ -22,7 +22,11 @@ struct TcState {
     int kernel = 2;               // 1 = single-CTA transposed kernel (mlp_tc.cu), 2 = CTA-pair kernel (mlp_tc2.cu)
     int pairs_post_v1 = 0;        // POST tile pairs the v1 kernel consumes (the pair kernel's zero lin_out tile excluded)
     int* table2 = nullptr;        // pair kernel: per-rank weight tile tables
-    int table2_parity = -1, uses2_pre = 0, uses2_post = 0, max_grid2 = 0;
+    int table2_parity = -1, uses2_zmap = 0, uses2_pre = 0, uses2_post = 0, max_grid2 = 0;
+    float* zmap = nullptr;        // pair kernel: Y_b = lin_z[b](latent) maps, [block][pixel][512] fp32 (hoisted lin_z, see mlp_tc2.cu)
+    size_t zmap_bytes = 0;
+    bool zmap_valid = false;      // cleared by diner_set_mlp / diner_set_scene; rebuilt lazily by the next query
+    float ms_zmap = 0.f;          // device time of the last Y-map build (timing enabled)
     CUtensorMap wmap;             // 2-D view of wpack: rows of 128 B, box = one 16 KiB tile (pair kernel: cta_group::2 TMA)
     bool wmap_ok = false;
     int dbg_skip = 0;             // profiling experiments (pair kernel PRE): see tc2::Args::dbg_skip

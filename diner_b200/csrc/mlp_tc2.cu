@@ -15,7 +15,13 @@
 // TMEM load, writes 16-byte K-major chunks into the next layer's A operand; the mean over views is a shuffle over
 // adjacent lanes; lin_out is an N=32 MMA whose 4 valid outputs land in the row's own thread.
 //
-// Reference semantics: src/models/resnetfc.py:61-69,129-159; src/models/pixelnerf.py:91-143.
+// lin_z is hoisted out of the per-sample work: grid_sample(bilinear) and lin_z are both linear, so
+//   lin_z[b](bilinear(latent, uv)) == bilinear(lin_z[b](latent), uv)      (the four tap weights sum to 1)
+// and Y_b = W_z[b] . latent is computed ONCE per (scene, weights) for every latent pixel by the ZMAP variant of this kernel
+// (bf16x3, fp32 maps [b][pixel][512]).  The PRE kernel then gathers Y_b bilinearly and adds it to the fp32 residual in TMEM:
+// one third of the per-sample-view GEMM work and weight streaming disappears.  Biases stay in the cumulative vectors.
+//
+// Reference semantics: src/models/resnetfc.py:61-69,129-159; src/models/pixelnerf.py:91-143; src/models/image_encoder.py:97-146.
 #include "mlp_tc.h"
 
 namespace tc2 {
@@ -37,6 +43,8 @@ using tc::tmem_ld32;
 using tc::tmem_ld32_issue;
 using tc::tmem_ld_wait;
 using tc::tmem_st32;
+using tc::tmem_st32_issue;
+using tc::tmem_st_wait;
 using tc::make_desc;
 using tc::split8;
 using tc::sample_point;
@@ -79,6 +87,9 @@ struct Args {
     int NV, spv;
     float* xc;                  // [sample][512] fp32 view-combined activations (sub-batch relative)
     float* out;
+    float* zmap;                // Y maps [block][pixel][512] fp32: PRE reads them, ZMAP writes them
+    long long zmap_stride;      // floats per block map = n_pix * 512
+    long long n_pix;            // ZMAP: latent pixels (SB*NV*Hl*Wl)
     int* err;
     long long* dbg_ts;          // profiling: clock64 stamps of pair 0 in round 1 ([cta][role][slot])
     int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
@@ -123,11 +134,13 @@ __device__ __forceinline__ uint32_t act_off(int r, int kc) {
     return (uint32_t)(kc >> 3) * ACT_KB_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((kc & 7) ^ (r & 7)) << 4);
 }
 
+// The lo-operand region exists in both modes: the gathered fp32 Y rows are staged across (A_hi, A_lo) chunk slots in place
+// (8 floats of (row, k-chunk) = 16 B in the hi slot + 16 B in the lo slot) before the epilogue turns them into operands.
 template <bool PARITY> struct Cfg {
-    static constexpr int NST = PARITY ? 6 : 8;
+    static constexpr int NST = 6;
     static constexpr int OFF_A_HI = NST * WTILE_BYTES;
     static constexpr int OFF_A_LO = OFF_A_HI + ACT_BYTES;
-    static constexpr int OFF_TAPS = OFF_A_LO + (PARITY ? ACT_BYTES : 0);
+    static constexpr int OFF_TAPS = OFF_A_LO + ACT_BYTES;
     static constexpr int OFF_BARS = OFF_TAPS + ROWS * (int)sizeof(RowTap);
     static constexpr int SMEM_BYTES = OFF_BARS + 256;
 };
@@ -221,20 +234,20 @@ __device__ __forceinline__ void prep_rows(const Args& a, long long tile, int wt,
     }
 }
 
-// PRE gather: bilinear latent of this warp's 8 rows -> A operand.  One row x 256 channels per pass: lane = 8 channels,
-// 32-byte loads per tap (1 KiB coalesced per warp), one 16-byte chunk store.
-template <bool PARITY>
-__device__ __forceinline__ void gather_latent(const Args& a, int wwarp, int lane, uint8_t* Ahi, uint8_t* Alo, const RowTap* taps) {
-    const SceneDev& s = a.s;
-    const int passes = s.L >> 8;
-    const int n_units = ROWS * passes;              // unit = (row, 256-channel pass); lane = 8 channels
+// PRE gather: bilinear Y_b (= lin_z[b] of the latent map) rows of this tile -> fp32 staging in the (A_hi, A_lo) chunk slots.
+// One row x 256 channels per pass: lane = 8 channels, 32-byte loads per tap (1 KiB coalesced per warp); channels 0..3 of the
+// lane's chunk go to the hi slot, 4..7 to the lo slot (the epilogue thread that owns the row reads exactly these slots back).
+__device__ __forceinline__ void gather_y(const SceneDev& s, const float* __restrict__ ymap, int wwarp, int lane, uint8_t* Ahi,
+                                         uint8_t* Alo, const RowTap* taps) {
+    constexpr int passes = HID >> 8;
+    constexpr int n_units = ROWS * passes;          // unit = (row, 256-channel pass); lane = 8 channels
     auto issue = [&](int u, float4 (&f)[8], float (&w)[4], uint32_t& off) {
         const int r = u / passes, p = u % passes;
         const RowTap rt = taps[r];
-        const size_t ox = (rt.dxy & 1) ? (size_t)s.L : 0, oy = (rt.dxy & 2) ? (size_t)s.Wl * s.L : 0;
+        const size_t ox = (rt.dxy & 1) ? (size_t)HID : 0, oy = (rt.dxy & 2) ? (size_t)s.Wl * HID : 0;
         w[0] = rt.ex * rt.ey; w[1] = rt.wx * rt.ey; w[2] = rt.ex * rt.wy; w[3] = rt.wx * rt.wy;
         const int k0 = 256 * p + 8 * lane;
-        const float* b00 = s.latent + (size_t)rt.pix00 * s.L + k0;
+        const float* b00 = ymap + (size_t)rt.pix00 * HID + k0;
         f[0] = __ldg((const float4*)b00); f[1] = __ldg((const float4*)(b00 + 4));
         f[2] = __ldg((const float4*)(b00 + ox)); f[3] = __ldg((const float4*)(b00 + ox + 4));
         f[4] = __ldg((const float4*)(b00 + oy)); f[5] = __ldg((const float4*)(b00 + oy + 4));
@@ -242,15 +255,13 @@ __device__ __forceinline__ void gather_latent(const Args& a, int wwarp, int lane
         off = act_off(r, k0 >> 3);
     };
     auto finish = [&](const float4 (&f)[8], const float (&w)[4], uint32_t off) {
-        float x[8];
-        x[0] = f[0].x * w[0] + f[2].x * w[1] + f[4].x * w[2] + f[6].x * w[3]; x[1] = f[0].y * w[0] + f[2].y * w[1] + f[4].y * w[2] + f[6].y * w[3];
-        x[2] = f[0].z * w[0] + f[2].z * w[1] + f[4].z * w[2] + f[6].z * w[3]; x[3] = f[0].w * w[0] + f[2].w * w[1] + f[4].w * w[2] + f[6].w * w[3];
-        x[4] = f[1].x * w[0] + f[3].x * w[1] + f[5].x * w[2] + f[7].x * w[3]; x[5] = f[1].y * w[0] + f[3].y * w[1] + f[5].y * w[2] + f[7].y * w[3];
-        x[6] = f[1].z * w[0] + f[3].z * w[1] + f[5].z * w[2] + f[7].z * w[3]; x[7] = f[1].w * w[0] + f[3].w * w[1] + f[5].w * w[2] + f[7].w * w[3];
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        *(uint4*)(Ahi + off) = hi;
-        if (PARITY) *(uint4*)(Alo + off) = lo;
+        float4 lo4, hi4;
+        lo4.x = f[0].x * w[0] + f[2].x * w[1] + f[4].x * w[2] + f[6].x * w[3]; lo4.y = f[0].y * w[0] + f[2].y * w[1] + f[4].y * w[2] + f[6].y * w[3];
+        lo4.z = f[0].z * w[0] + f[2].z * w[1] + f[4].z * w[2] + f[6].z * w[3]; lo4.w = f[0].w * w[0] + f[2].w * w[1] + f[4].w * w[2] + f[6].w * w[3];
+        hi4.x = f[1].x * w[0] + f[3].x * w[1] + f[5].x * w[2] + f[7].x * w[3]; hi4.y = f[1].y * w[0] + f[3].y * w[1] + f[5].y * w[2] + f[7].y * w[3];
+        hi4.z = f[1].z * w[0] + f[3].z * w[1] + f[5].z * w[2] + f[7].z * w[3]; hi4.w = f[1].w * w[0] + f[3].w * w[1] + f[5].w * w[2] + f[7].w * w[3];
+        *(float4*)(Ahi + off) = lo4;                // channels k0..k0+3
+        *(float4*)(Alo + off) = hi4;                // channels k0+4..k0+7
     };
 #pragma unroll 1
     for (int u = wwarp; u < n_units; u += 2 * NUM_OPND_WARPS) {
@@ -262,6 +273,91 @@ __device__ __forceinline__ void gather_latent(const Args& a, int wwarp, int lane
         if (two) issue(u + NUM_OPND_WARPS, fb, wb, ob);
         finish(fa, wa, oa);
         if (two) finish(fb, wb, ob);
+    }
+}
+
+// Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row), written back to TMEM as
+// the residual; relu(x' + cumulative bias) -> bf16 hi/lo chunks of the fc_0 operand.  Each thread reads and then overwrites
+// only its own (row, k-chunk) slots, so the staging can live in the operand buffers.
+template <bool PARITY>
+__device__ __forceinline__ void add32_convert(uint32_t* v, const float* __restrict__ bias, int h0, int r, uint8_t* Ahi, uint8_t* Alo) {
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+        const uint32_t off = act_off(r, (h0 >> 3) + c8);
+        const float4 g0 = *(const float4*)(Ahi + off), g1 = *(const float4*)(Alo + off);
+        const float4 b0 = __ldg((const float4*)(bias + h0 + 8 * c8)), b1 = __ldg((const float4*)(bias + h0 + 8 * c8 + 4));
+        float xs[8], x[8];
+        xs[0] = __uint_as_float(v[8 * c8 + 0]) + g0.x; xs[1] = __uint_as_float(v[8 * c8 + 1]) + g0.y;
+        xs[2] = __uint_as_float(v[8 * c8 + 2]) + g0.z; xs[3] = __uint_as_float(v[8 * c8 + 3]) + g0.w;
+        xs[4] = __uint_as_float(v[8 * c8 + 4]) + g1.x; xs[5] = __uint_as_float(v[8 * c8 + 5]) + g1.y;
+        xs[6] = __uint_as_float(v[8 * c8 + 6]) + g1.z; xs[7] = __uint_as_float(v[8 * c8 + 7]) + g1.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * c8 + i] = __float_as_uint(xs[i]);
+        x[0] = fmaxf(xs[0] + b0.x, 0.0f); x[1] = fmaxf(xs[1] + b0.y, 0.0f); x[2] = fmaxf(xs[2] + b0.z, 0.0f); x[3] = fmaxf(xs[3] + b0.w, 0.0f);
+        x[4] = fmaxf(xs[4] + b1.x, 0.0f); x[5] = fmaxf(xs[5] + b1.y, 0.0f); x[6] = fmaxf(xs[6] + b1.z, 0.0f); x[7] = fmaxf(xs[7] + b1.w, 0.0f);
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        *(uint4*)(Ahi + off) = hi;
+        if (PARITY) *(uint4*)(Alo + off) = lo;
+    }
+}
+template <bool PARITY>
+__device__ __forceinline__ void epilogue_add_y(uint32_t tmem, const float* __restrict__ bias, uint8_t* Ahi, uint8_t* Alo, int q,
+                                               int lane, int n2) {
+    const int r = 32 * (q & 1) + lane;
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2);
+    const int hb = 256 * n2 + 128 * (q >> 1);
+    uint32_t va[32], vb[32];
+    tmem_ld32_issue(t0, va);
+    tmem_ld32_issue(t0 + 32, vb);
+    tmem_ld_wait();
+    add32_convert<PARITY>(va, bias, hb, r, Ahi, Alo);
+    tmem_st32_issue(t0, va);
+    add32_convert<PARITY>(vb, bias, hb + 32, r, Ahi, Alo);
+    tmem_st32_issue(t0 + 32, vb);
+    tmem_st_wait();                                 // va / vb are reused as load destinations below
+    tmem_ld32_issue(t0 + 64, va);
+    tmem_ld32_issue(t0 + 96, vb);
+    tmem_ld_wait();
+    add32_convert<PARITY>(va, bias, hb + 64, r, Ahi, Alo);
+    tmem_st32_issue(t0 + 64, va);
+    add32_convert<PARITY>(vb, bias, hb + 96, r, Ahi, Alo);
+    tmem_st32_issue(t0 + 96, vb);
+    tmem_st_wait();
+}
+
+// ZMAP: 64 latent pixels (rows) x L channels -> bf16 hi/lo A operand; consecutive threads take consecutive 8-channel chunks
+__device__ __forceinline__ void load_latent_rows(const Args& a, long long tile, int wt, uint8_t* Ahi, uint8_t* Alo) {
+    const int cpr = a.s.L >> 3;                     // 8-channel chunks per row
+#pragma unroll 2
+    for (int i = wt; i < ROWS * cpr; i += NUM_OPND_WARPS * 32) {
+        const int r = i / cpr, kc = i % cpr;
+        long long pix = tile * ROWS + r;
+        if (pix >= a.n_pix) pix = a.n_pix - 1;
+        const float4* src = (const float4*)(a.s.latent + (size_t)pix * a.s.L + 8 * kc);
+        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
+        const float x[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = act_off(r, kc);
+        *(uint4*)(Ahi + off) = hi;
+        *(uint4*)(Alo + off) = lo;
+    }
+}
+// ZMAP: accumulator rows -> Y_b[pixel][512] fp32 (thread = row, 128 contiguous bytes per TMEM load)
+__device__ __forceinline__ void store_y_rows(uint32_t tmem, float* __restrict__ ymap, long long pix, bool write, int q, int lane, int n2) {
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2);
+    const int hb = 256 * n2 + 128 * (q >> 1);
+#pragma unroll 1
+    for (int c32 = 0; c32 < 4; ++c32) {
+        uint32_t v[32];
+        tmem_ld32(t0 + 32 * c32, v);
+        if (write) {
+            float4* dst = (float4*)(ymap + (size_t)pix * HID + hb + 32 * c32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
     }
 }
 
@@ -325,9 +421,11 @@ __device__ __forceinline__ void worker_arrive(uint32_t bar_local, uint32_t bar_l
 #define TS(role, slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == 1 && lane == 0) a.dbg_ts[(blockIdx.x * 4 + (role)) * 64 + (slot)] = clock64(); } while (0)
 #define TSW() do { if (a.dbg_ts && blockIdx.x < 2 && rd == 1 && wwarp == 0 && lane == 0 && tsn < 64) a.dbg_ts[(blockIdx.x * 4 + 1) * 64 + tsn++] = clock64(); } while (0)
 // ---- the kernel ----------------------------------------------------------------------------------
-template <bool PARITY, bool POST>
+constexpr int KIND_PRE = 0, KIND_POST = 1, KIND_ZMAP = 2;
+template <bool PARITY, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_pair_kernel(const __grid_constant__ Args a) {
     using C = Cfg<PARITY>;
+    constexpr bool POST = KIND == KIND_POST;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
@@ -458,17 +556,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             const long long tile_raw = first + rd * stride;
             const bool live = tile_raw < a.n_tiles;
             const long long tile = live ? tile_raw : a.n_tiles - 1;
-            if constexpr (!POST) {
+            if constexpr (KIND == KIND_ZMAP) {
+                // Y_b = W_z[b] . latent for the 64 latent pixels of this tile (once per scene x weights)
+                load_latent_rows(a, tile, wt, Ahi, Alo);
+                worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                       // -> lin_z[0]
+                const long long pix = tile * ROWS + r;
+                for (int b = 0; b < a.n_blocks; ++b) {
+                    mbar_wait(bar_acc, it & 1, a.err, 44); ++it;
+                    tc_fence_after();
+                    if (!helper) store_y_rows(tmem, a.zmap + (size_t)b * a.zmap_stride, pix, live && pix < a.n_pix, q, lane, n2);
+                    tc_fence_before();
+                    if (b + 1 < a.n_blocks) worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);           // X free -> lin_z[b+1]
+                }
+            } else if constexpr (!POST) {
                 if (!(a.dbg_skip & 4)) prep_rows<PARITY>(a, tile, wt, Ahi, Alo, taps);
                 TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> lin_in
                 for (int b = 0; b < a.n_blocks; ++b) {
                     if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 40); else mbar_wait(bar_acc, it & 1, a.err, 40); ++it; TSW();
                     tc_fence_after();
-                    if (!(a.dbg_skip & 1)) gather_latent<PARITY>(a, wwarp, lane, Ahi, Alo, taps);
-                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> lin_z[b]
-                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 41); else mbar_wait(bar_acc, it & 1, a.err, 41); ++it; TSW();
-                    tc_fence_after();
-                    if (!helper && !(a.dbg_skip & 2)) epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2);
+                    // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gather into the (now idle) operand buffers, then add in the epilogue
+                    if (!(a.dbg_skip & 1)) gather_y(a.s, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, taps);
+                    asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // staging complete
+                    TSW();
+                    if (!helper && !(a.dbg_skip & 2)) epilogue_add_y<PARITY>(tmem, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2);
                     TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_0[b]
                     if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 42); else mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
                     tc_fence_after();
@@ -564,9 +674,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     }
 }
 
-template <bool PARITY, bool POST>
+template <bool PARITY, int KIND>
 cudaError_t launch(const Args& a, int grid, cudaStream_t st) {
-    auto kern = mlp_pair_kernel<PARITY, POST>;
+    auto kern = mlp_pair_kernel<PARITY, KIND>;
     constexpr int smem = Cfg<PARITY>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
@@ -581,51 +691,50 @@ cudaError_t launch(const Args& a, int grid, cudaStream_t st) {
 
 }  // namespace tc2
 
-// host: the pair kernel shares tc_pack_weights' tile stream; this builds the per-rank tile tables and launches
-cudaError_t tc2_prepare(TcState& t, const MlpDev& m, bool parity_table, cudaStream_t st);
-
-cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity, int num_sms,
-                      cudaStream_t st) {
+// Per-rank weight tile tables of the pair kernel.  Ring-use order of CTA rank r = for each GEMM step, for n2, for kb:
+// tile (2*n2 + r) of that layer; every entry is a 16 KiB tile index into the packed stream ([hi][lo] per tile pair).
+// Layout of t.table2: [zmap r0][zmap r1][pre r0][pre r1][post r0][post r1]; zmap is always bf16x3.
+static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cudaStream_t st) {
     using namespace tc2;
-    const int NV = s.NV;
-    if (NV > 32 || (32 % NV)) { snprintf(t.why, sizeof(t.why), "NV=%d views (tcgen05 path needs NV in {1,2,4,8,16,32})", NV); return cudaErrorNotSupported; }
-    if (s.L != m.d_latent || (s.L % 256)) { snprintf(t.why, sizeof(t.why), "pair kernel needs d_latent %% 256 == 0 (got %d)", s.L); return cudaErrorNotSupported; }
-    const int d_in = 3 + 6 * s.num_freqs + 3 + 1 + 2 * s.num_freqs;
-    if (d_in != m.d_in) { snprintf(t.why, sizeof(t.why), "positional code gives d_in=%d but lin_in expects %d", d_in, m.d_in); return cudaErrorNotSupported; }
-    const long long total = (long long)q.SB * q.n_per_sb;
     const int kbz = m.d_latent / KBLK, kbh = HID / KBLK;
-
-    // per-rank tile tables: ring-use order of CTA rank r = for each step, for n2, for kb: tile (2*n2 + r) of that layer
-    if (!t.table2 || t.table2_parity != (int)parity) {
-        std::vector<int> tab[2];
-        int layer_pair0 = 0;
-        auto layer = [&](int nkb, int n_mt, int n_tiles) {
+    std::vector<int> zm[2], pre[2], post[2];
+    int layer_pair0 = 0;
+    auto layer = [&](std::vector<int>* tab, bool par, int nkb, int n_mt, int n_tiles) {
+        if (tab)
             for (int r = 0; r < 2; ++r)
                 for (int n2 = 0; n2 < n_tiles; ++n2)
                     for (int kb = 0; kb < nkb; ++kb) {
                         const int pair = layer_pair0 + (2 * n2 + r) * nkb + kb;
                         tab[r].push_back(2 * pair);
-                        if (parity) tab[r].push_back(2 * pair + 1);
+                        if (par) tab[r].push_back(2 * pair + 1);
                     }
-            layer_pair0 += n_mt * nkb;
-        };
-        layer(1, 4, 2);                                              // lin_in
-        for (int b = 0; b < t.n_pre; ++b) { layer(kbz, 4, 2); layer(kbh, 4, 2); layer(kbh, 4, 2); }
-        t.uses2_pre = (int)tab[0].size();
-        for (int b = 0; b < t.n_post; ++b) { layer(kbh, 4, 2); layer(kbh, 4, 2); }
-        layer(kbh, 2, 1);                                            // lin_out packed as 2 M-tiles (second is zeros)
-        t.uses2_post = (int)tab[0].size() - t.uses2_pre;
-        std::vector<int> flat;                                       // [pre r0][pre r1][post r0][post r1]
-        for (int r = 0; r < 2; ++r) flat.insert(flat.end(), tab[r].begin(), tab[r].begin() + t.uses2_pre);
-        for (int r = 0; r < 2; ++r) flat.insert(flat.end(), tab[r].begin() + t.uses2_pre, tab[r].end());
-        if (!t.table2) TCK(cudaMalloc((void**)&t.table2, 4096 * sizeof(int)));
-        if (flat.size() > 4096) return cudaErrorInvalidValue;
-        TCK(cudaMemcpyAsync(t.table2, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        TCK(cudaStreamSynchronize(st));                              // `flat` is a stack-lifetime host buffer
-        t.table2_parity = (int)parity;
+        layer_pair0 += n_mt * nkb;
+    };
+    layer(pre, parity, 1, 4, 2);                                     // lin_in
+    for (int b = 0; b < t.n_pre; ++b) {
+        layer(zm, true, kbz, 4, 2);                                  // lin_z[b]: hoisted into the per-scene Y maps
+        layer(pre, parity, kbh, 4, 2);                               // fc_0[b]
+        layer(pre, parity, kbh, 4, 2);                               // fc_1[b]
     }
+    for (int b = 0; b < t.n_post; ++b) { layer(post, parity, kbh, 4, 2); layer(post, parity, kbh, 4, 2); }
+    layer(post, parity, kbh, 2, 1);                                  // lin_out packed as 2 M-tiles (second is zeros)
+    t.uses2_zmap = (int)zm[0].size(); t.uses2_pre = (int)pre[0].size(); t.uses2_post = (int)post[0].size();
+    std::vector<int> flat;
+    for (int r = 0; r < 2; ++r) flat.insert(flat.end(), zm[r].begin(), zm[r].end());
+    for (int r = 0; r < 2; ++r) flat.insert(flat.end(), pre[r].begin(), pre[r].end());
+    for (int r = 0; r < 2; ++r) flat.insert(flat.end(), post[r].begin(), post[r].end());
+    if (flat.size() > 8192) return cudaErrorInvalidValue;
+    if (!t.table2) TCK(cudaMalloc((void**)&t.table2, 8192 * sizeof(int)));
+    TCK(cudaMemcpyAsync(t.table2, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    TCK(cudaStreamSynchronize(st));                                  // `flat` is a stack-lifetime host buffer
+    t.table2_parity = (int)parity;
+    return cudaSuccess;
+}
+
+static cudaError_t tc2_grid_cap(TcState& t, int num_sms, int* cap) {
+    using namespace tc2;
     if (t.max_grid2 == 0) {
-        auto kern = mlp_pair_kernel<true, false>;
+        auto kern = mlp_pair_kernel<true, KIND_PRE>;
         TCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(128); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = Cfg<true>::SMEM_BYTES;
@@ -633,7 +742,64 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = num_sms / 2; }
         t.max_grid2 = n > 0 ? 2 * n : 2;
     }
-    const int grid_cap = t.max_grid2 < (num_sms / 2) * 2 ? t.max_grid2 : (num_sms / 2) * 2;
+    *cap = t.max_grid2 < (num_sms / 2) * 2 ? t.max_grid2 : (num_sms / 2) * 2;
+    return cudaSuccess;
+}
+
+// Y_b = W_z[b] . latent for every latent pixel (bf16x3): once per (scene, weights); see the header comment.
+static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int grid_cap, cudaStream_t st) {
+    using namespace tc2;
+    const long long n_pix = (long long)s.SB * s.NV * s.Hl * s.Wl;
+    const size_t need = (size_t)t.n_pre * n_pix * HID * sizeof(float);
+    if (need > t.zmap_bytes) {
+        if (t.zmap) cudaFree(t.zmap);
+        t.zmap = nullptr; t.zmap_bytes = 0;
+        TCK(cudaMalloc((void**)&t.zmap, need));
+        t.zmap_bytes = need;
+    }
+    Args z{};
+    z.wmap = t.wmap;
+    z.s = s;
+    z.wstream = (const uint8_t*)t.wpack;
+    z.tile_table = t.table2;
+    z.uses_per_tile = t.uses2_zmap;
+    z.bias = t.bias;
+    z.n_blocks = t.n_pre;
+    for (int b = 0; b < t.n_pre; ++b) z.steps[b] = GemmStep{(short)(m.d_latent / KBLK), 2, 256, COL_X, 0};
+    z.n_steps = t.n_pre;
+    z.zmap = t.zmap; z.zmap_stride = n_pix * HID; z.n_pix = n_pix;
+    z.n_tiles = (n_pix + ROWS - 1) / ROWS;
+    z.NV = s.NV; z.spv = ROWS / s.NV;
+    z.err = t.err_flag;
+    const long long g = ((z.n_tiles + 1) / 2) * 2;
+    if (t.timing) TCK(cudaEventRecord(t.ev[0], st));
+    TCK((launch<true, KIND_ZMAP>(z, (int)(g < grid_cap ? g : grid_cap), st)));
+    if (t.timing) {
+        TCK(cudaEventRecord(t.ev[1], st));
+        TCK(cudaEventSynchronize(t.ev[1]));
+        TCK(cudaEventElapsedTime(&t.ms_zmap, t.ev[0], t.ev[1]));
+    }
+    t.zmap_valid = true;
+    return cudaSuccess;
+}
+
+cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity, int num_sms,
+                      cudaStream_t st) {
+    using namespace tc2;
+    const int NV = s.NV;
+    if (NV > 32 || (32 % NV)) { snprintf(t.why, sizeof(t.why), "NV=%d views (tcgen05 path needs NV in {1,2,4,8,16,32})", NV); return cudaErrorNotSupported; }
+    if (s.L != m.d_latent || (s.L % KBLK) || s.L > HID) { snprintf(t.why, sizeof(t.why), "pair kernel needs d_latent == latent channels, %% 64 == 0, <= 512 (got %d / %d)", m.d_latent, s.L); return cudaErrorNotSupported; }
+    const int d_in = 3 + 6 * s.num_freqs + 3 + 1 + 2 * s.num_freqs;
+    if (d_in != m.d_in) { snprintf(t.why, sizeof(t.why), "positional code gives d_in=%d but lin_in expects %d", d_in, m.d_in); return cudaErrorNotSupported; }
+    if (!t.wmap_ok) { snprintf(t.why, sizeof(t.why), "cuTensorMapEncodeTiled unavailable"); return cudaErrorNotSupported; }
+    const long long total = (long long)q.SB * q.n_per_sb;
+    const int kbh = HID / KBLK;
+
+    if (!t.table2 || t.table2_parity != (int)parity) TCK(tc2_build_tables(t, m, parity, st));
+    int grid_cap = 2;
+    TCK(tc2_grid_cap(t, num_sms, &grid_cap));
+    if (t.timing && !t.ev[0]) for (int i = 0; i < 4; ++i) TCK(cudaEventCreate(&t.ev[i]));
+    if (!t.zmap_valid) TCK(tc2_zmap(t, s, m, grid_cap, st));
     const long long sub = t.sub_batch > 0 ? t.sub_batch : 524288;
     const size_t need = (size_t)(((sub + ROWS - 1) / ROWS) * ROWS) * HID * sizeof(float);
     if (need > t.scratch_bytes) {
@@ -643,18 +809,17 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         t.scratch_bytes = need;
     }
     Args pre{}, post{};
-    if (!t.wmap_ok) { snprintf(t.why, sizeof(t.why), "cuTensorMapEncodeTiled unavailable"); return cudaErrorNotSupported; }
     pre.wmap = post.wmap = t.wmap;
     pre.s = s; pre.q = q; post.s = s; post.q = q;
     pre.wstream = post.wstream = (const uint8_t*)t.wpack;
-    pre.tile_table = t.table2; post.tile_table = t.table2 + 2 * t.uses2_pre;
+    pre.tile_table = t.table2 + 2 * t.uses2_zmap; post.tile_table = pre.tile_table + 2 * t.uses2_pre;
     pre.uses_per_tile = t.uses2_pre; post.uses_per_tile = t.uses2_post;
     pre.bias = t.bias; post.bias = t.bias + t.bias_post_off;
     pre.n_blocks = t.n_pre; post.n_blocks = t.n_post;
+    pre.zmap = t.zmap; pre.zmap_stride = (long long)s.SB * s.NV * s.Hl * s.Wl * HID;
     int n = 0;
     pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0};
     for (int b = 0; b < t.n_pre; ++b) {
-        pre.steps[n++] = GemmStep{(short)kbz, 2, 256, COL_X, 1};
         pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0};
         pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1};
     }
@@ -677,7 +842,6 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     if ((t.dbg_skip & 512) && !dbg_ts) { TCK(cudaMallocManaged((void**)&dbg_ts, 8 * 64 * sizeof(long long))); memset(dbg_ts, 0, 8 * 64 * sizeof(long long)); }
     pre.dbg_ts = (t.dbg_skip & 512) ? dbg_ts : nullptr; post.dbg_ts = nullptr;
     t.ms_pre = t.ms_post = 0.f;
-    if (t.timing && !t.ev[0]) for (int i = 0; i < 4; ++i) TCK(cudaEventCreate(&t.ev[i]));
     for (long long s0 = 0; s0 < total; s0 += sub) {
         const long long ns = total - s0 < sub ? total - s0 : sub;
         pre.s_begin = post.s_begin = s0;
@@ -687,9 +851,9 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         const long long g1 = ((pre.n_tiles + 1) / 2) * 2, g2 = ((post.n_tiles + 1) / 2) * 2;
         const int grid1 = (int)(g1 < grid_cap ? g1 : grid_cap), grid2 = (int)(g2 < grid_cap ? g2 : grid_cap);
         if (t.timing) TCK(cudaEventRecord(t.ev[0], st));
-        if (parity) TCK((launch<true, false>(pre, grid1, st))); else TCK((launch<false, false>(pre, grid1, st)));
+        if (parity) TCK((launch<true, KIND_PRE>(pre, grid1, st))); else TCK((launch<false, KIND_PRE>(pre, grid1, st)));
         if (t.timing) TCK(cudaEventRecord(t.ev[1], st));
-        if (parity) TCK((launch<true, true>(post, grid2, st))); else TCK((launch<false, true>(post, grid2, st)));
+        if (parity) TCK((launch<true, KIND_POST>(post, grid2, st))); else TCK((launch<false, KIND_POST>(post, grid2, st)));
         if (t.timing) {
             TCK(cudaEventRecord(t.ev[2], st));
             TCK(cudaEventSynchronize(t.ev[2]));

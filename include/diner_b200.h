@@ -109,7 +109,7 @@ int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, i
 
 /* Tuning knobs of the tcgen05 path (not part of the reference API): key = "cluster" (thread-block cluster size for
  * weight multicast of kernel 1: 1, 2 or 4), "kernel" (1 = single-CTA tcgen05 kernel, 2 = CTA-pair cta_group::2 kernel, default)
- * or "sub_batch" (samples per PRE/POST launch pair). */
+ * "sub_batch" (samples per PRE/POST launch pair) or "rebuild_maps" (forces the next query to rebuild the hoisted lin_z maps). */
 int diner_set_option(diner_ctx* ctx, const char* key, long long value);
 
 /* cudaDeviceSynchronize + decoded tcgen05 watchdog code on failure (debugging aid). */
@@ -122,7 +122,8 @@ long long diner_launch_count(diner_ctx* ctx);
 int diner_set_timing(diner_ctx* ctx, int enabled);
 float diner_last_mlp_ms(diner_ctx* ctx);
 /* Per-stage device time of the last call (timing enabled): 0 sampler, 1 MLP PRE kernel(s) (per sample-view layers),
- * 2 MLP POST kernel(s) (per sample layers), 3 compositing. */
+ * 2 MLP POST kernel(s) (per sample layers), 3 compositing, 4 the once-per-(scene, weights) build of the hoisted lin_z maps
+ * (runs inside the first query after diner_set_scene / diner_set_mlp). */
 float diner_last_stage_ms(diner_ctx* ctx, int stage);
 
 #ifdef __cplusplus
