@@ -72,6 +72,7 @@ struct GemmStep {
     short n_width;     // UMMA N: 256, or 32 for lin_out
     short dst_col;     // TMEM column base
     short accumulate;
+    short release;     // commit the per-K-block "A operand free" barriers (the step is followed by a gather into A)
 };
 
 struct Args {
@@ -165,25 +166,22 @@ __device__ __forceinline__ void convert32(const uint32_t* v, const float* __rest
         if (PARITY) *(uint4*)(Alo + off) = lo;
     }
 }
-// TMEM region (this warp's N tile: 128 columns) + per-column bias -> relu -> bf16 hi/lo chunks of the A operand.
-// Two TMEM loads are kept in flight (the second 64 columns load while the first are converted).
+// Epilogues run in two HALVES so that the next GEMM (K-block-outer order) starts on K blocks 0..3 while the workers still
+// convert K blocks 4..7.  In half h every worker warp (q = TMEM lane quarter, j = 0/1) owns 64 accumulator columns:
+//   TMEM lanes 32q..32q+31 (row = 32*(q&1) + lane), columns colbase + 128*h + 64*j + [0,64)
+//   = hidden units 256*h + 128*(q>>1) + 64*j + [0,64) = K block 4*h + 2*(q>>1) + j of the next layer's A operand.
 template <bool PARITY>
-__device__ __forceinline__ void epilogue_to_A(uint32_t tmem, int colbase, const float* __restrict__ bias, uint8_t* Ahi,
-                                              uint8_t* Alo, int q, int lane, int n2) {
+__device__ __forceinline__ void epilogue_half(uint32_t tmem, int colbase, const float* __restrict__ bias, uint8_t* Ahi,
+                                              uint8_t* Alo, int q, int lane, int j, int h) {
     const int r = 32 * (q & 1) + lane;
-    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(colbase + 128 * n2);
-    const int hb = 256 * n2 + 128 * (q >> 1);
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(colbase + 128 * h + 64 * j);
+    const int hb = 256 * h + 128 * (q >> 1) + 64 * j;
     uint32_t va[32], vb[32];
     tmem_ld32_issue(t0, va);
     tmem_ld32_issue(t0 + 32, vb);
     tmem_ld_wait();
     convert32<PARITY>(va, bias, hb, r, Ahi, Alo);
-    tmem_ld32_issue(t0 + 64, va);
     convert32<PARITY>(vb, bias, hb + 32, r, Ahi, Alo);
-    tmem_ld32_issue(t0 + 96, vb);
-    tmem_ld_wait();
-    convert32<PARITY>(va, bias, hb + 64, r, Ahi, Alo);
-    convert32<PARITY>(vb, bias, hb + 96, r, Ahi, Alo);
 }
 
 // PRE prep: 4 threads per row -> lin_in A operand (K block 0) + bilinear tap set
@@ -234,19 +232,22 @@ __device__ __forceinline__ void prep_rows(const Args& a, long long tile, int wt,
     }
 }
 
-// PRE gather: bilinear Y_b (= lin_z[b] of the latent map) rows of this tile -> fp32 staging in the (A_hi, A_lo) chunk slots.
-// One row x 256 channels per pass: lane = 8 channels, 32-byte loads per tap (1 KiB coalesced per warp); channels 0..3 of the
-// lane's chunk go to the hi slot, 4..7 to the lo slot (the epilogue thread that owns the row reads exactly these slots back).
-__device__ __forceinline__ void gather_y(const SceneDev& s, const float* __restrict__ ymap, int wwarp, int lane, uint8_t* Ahi,
-                                         uint8_t* Alo, const RowTap* taps) {
-    constexpr int passes = HID >> 8;
-    constexpr int n_units = ROWS * passes;          // unit = (row, 256-channel pass); lane = 8 channels
-    auto issue = [&](int u, float4 (&f)[8], float (&w)[4], uint32_t& off) {
-        const int r = u / passes, p = u % passes;
+// PRE gather: bilinear Y_b (= lin_z[b] of the latent map) rows of this tile -> fp32 staging in the (A_hi, A_lo) chunk slots,
+// in K-BLOCK ORDER and overlapped with the GEMM that is still reading the operand buffers: before touching K block kb the warp
+// waits on bar_afree[kb], which the MMA issuer commits right after the last MMA that reads that K block.
+// One pass = 4 rows x 64 channels (one K block): lane -> row 4*(p%16) + lane/8, 8 channels (lane%8): 32-byte loads per tap;
+// channels 0..3 of the chunk go to the hi slot, 4..7 to the lo slot (the epilogue thread that owns the row reads them back).
+__device__ __forceinline__ void gather_y(const Args& a, const float* __restrict__ ymap, int wwarp, int lane, uint8_t* Ahi,
+                                         uint8_t* Alo, const RowTap* taps, uint32_t bar_afree, uint32_t parity) {
+    const SceneDev& s = a.s;
+    constexpr int PASSES_PER_KB = ROWS / 4;         // 16
+    constexpr int n_passes = PASSES_PER_KB * (HID / KBLK);   // 128
+    auto issue = [&](int p, float4 (&f)[8], float (&w)[4], uint32_t& off) {
+        const int kb = p / PASSES_PER_KB, r = 4 * (p % PASSES_PER_KB) + (lane >> 3);
         const RowTap rt = taps[r];
         const size_t ox = (rt.dxy & 1) ? (size_t)HID : 0, oy = (rt.dxy & 2) ? (size_t)s.Wl * HID : 0;
         w[0] = rt.ex * rt.ey; w[1] = rt.wx * rt.ey; w[2] = rt.ex * rt.wy; w[3] = rt.wx * rt.wy;
-        const int k0 = 256 * p + 8 * lane;
+        const int k0 = KBLK * kb + 8 * (lane & 7);
         const float* b00 = ymap + (size_t)rt.pix00 * HID + k0;
         f[0] = __ldg((const float4*)b00); f[1] = __ldg((const float4*)(b00 + 4));
         f[2] = __ldg((const float4*)(b00 + ox)); f[3] = __ldg((const float4*)(b00 + ox + 4));
@@ -255,25 +256,30 @@ __device__ __forceinline__ void gather_y(const SceneDev& s, const float* __restr
         off = act_off(r, k0 >> 3);
     };
     auto finish = [&](const float4 (&f)[8], const float (&w)[4], uint32_t off) {
-        float4 lo4, hi4;
-        lo4.x = f[0].x * w[0] + f[2].x * w[1] + f[4].x * w[2] + f[6].x * w[3]; lo4.y = f[0].y * w[0] + f[2].y * w[1] + f[4].y * w[2] + f[6].y * w[3];
-        lo4.z = f[0].z * w[0] + f[2].z * w[1] + f[4].z * w[2] + f[6].z * w[3]; lo4.w = f[0].w * w[0] + f[2].w * w[1] + f[4].w * w[2] + f[6].w * w[3];
-        hi4.x = f[1].x * w[0] + f[3].x * w[1] + f[5].x * w[2] + f[7].x * w[3]; hi4.y = f[1].y * w[0] + f[3].y * w[1] + f[5].y * w[2] + f[7].y * w[3];
-        hi4.z = f[1].z * w[0] + f[3].z * w[1] + f[5].z * w[2] + f[7].z * w[3]; hi4.w = f[1].w * w[0] + f[3].w * w[1] + f[5].w * w[2] + f[7].w * w[3];
-        *(float4*)(Ahi + off) = lo4;                // channels k0..k0+3
-        *(float4*)(Alo + off) = hi4;                // channels k0+4..k0+7
+        float4 c03, c47;
+        c03.x = f[0].x * w[0] + f[2].x * w[1] + f[4].x * w[2] + f[6].x * w[3]; c03.y = f[0].y * w[0] + f[2].y * w[1] + f[4].y * w[2] + f[6].y * w[3];
+        c03.z = f[0].z * w[0] + f[2].z * w[1] + f[4].z * w[2] + f[6].z * w[3]; c03.w = f[0].w * w[0] + f[2].w * w[1] + f[4].w * w[2] + f[6].w * w[3];
+        c47.x = f[1].x * w[0] + f[3].x * w[1] + f[5].x * w[2] + f[7].x * w[3]; c47.y = f[1].y * w[0] + f[3].y * w[1] + f[5].y * w[2] + f[7].y * w[3];
+        c47.z = f[1].z * w[0] + f[3].z * w[1] + f[5].z * w[2] + f[7].z * w[3]; c47.w = f[1].w * w[0] + f[3].w * w[1] + f[5].w * w[2] + f[7].w * w[3];
+        *(float4*)(Ahi + off) = c03;                // channels k0..k0+3
+        *(float4*)(Alo + off) = c47;                // channels k0+4..k0+7
     };
+    int waited = -1;                                // highest K block whose "free" barrier this warp has passed
 #pragma unroll 1
-    for (int u = wwarp; u < n_units; u += 2 * NUM_OPND_WARPS) {
+    for (int p = wwarp; p < n_passes; p += 2 * NUM_OPND_WARPS) {
         float4 fa[8], fb[8];
         float wa[4], wb[4];
         uint32_t oa, ob = 0;
-        const bool two = u + NUM_OPND_WARPS < n_units;
-        issue(u, fa, wa, oa);
-        if (two) issue(u + NUM_OPND_WARPS, fb, wb, ob);
+        const int p2 = p + NUM_OPND_WARPS;
+        const bool two = p2 < n_passes;
+        const int kb_need = (two ? p2 : p) / PASSES_PER_KB;
+        while (waited < kb_need) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 45); }
+        issue(p, fa, wa, oa);
+        if (two) issue(p2, fb, wb, ob);
         finish(fa, wa, oa);
         if (two) finish(fb, wb, ob);
     }
+    while (waited < HID / KBLK - 1) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 46); }   // keep every warp's phase count in step
 }
 
 // Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row), written back to TMEM as
@@ -302,11 +308,11 @@ __device__ __forceinline__ void add32_convert(uint32_t* v, const float* __restri
     }
 }
 template <bool PARITY>
-__device__ __forceinline__ void epilogue_add_y(uint32_t tmem, const float* __restrict__ bias, uint8_t* Ahi, uint8_t* Alo, int q,
-                                               int lane, int n2) {
+__device__ __forceinline__ void epilogue_add_y_half(uint32_t tmem, const float* __restrict__ bias, uint8_t* Ahi, uint8_t* Alo, int q,
+                                                    int lane, int j, int h) {
     const int r = 32 * (q & 1) + lane;
-    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2);
-    const int hb = 256 * n2 + 128 * (q >> 1);
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * h + 64 * j);
+    const int hb = 256 * h + 128 * (q >> 1) + 64 * j;
     uint32_t va[32], vb[32];
     tmem_ld32_issue(t0, va);
     tmem_ld32_issue(t0 + 32, vb);
@@ -315,14 +321,6 @@ __device__ __forceinline__ void epilogue_add_y(uint32_t tmem, const float* __res
     tmem_st32_issue(t0, va);
     add32_convert<PARITY>(vb, bias, hb + 32, r, Ahi, Alo);
     tmem_st32_issue(t0 + 32, vb);
-    tmem_st_wait();                                 // va / vb are reused as load destinations below
-    tmem_ld32_issue(t0 + 64, va);
-    tmem_ld32_issue(t0 + 96, vb);
-    tmem_ld_wait();
-    add32_convert<PARITY>(va, bias, hb + 64, r, Ahi, Alo);
-    tmem_st32_issue(t0 + 64, va);
-    add32_convert<PARITY>(vb, bias, hb + 96, r, Ahi, Alo);
-    tmem_st32_issue(t0 + 96, vb);
     tmem_st_wait();
 }
 
@@ -403,18 +401,22 @@ __device__ __forceinline__ void combine_store(uint32_t* raw, const float* __rest
     }
 }
 
-// Operand hand-off to the MMA issuer (leader CTA).  Remote mbarrier arrives are slow (~1 us each and they serialise),
-// so the peer CTA first joins its 12 operand warps on a named barrier and sends ONE remote arrive; the leader's own
-// warps arrive locally.  Leader barrier count = NUM_OPND_WARPS + 1.
-__device__ __forceinline__ void worker_arrive(uint32_t bar_local, uint32_t bar_leader_remote, bool is_leader_cta, int wwarp, int lane) {
+// Operand hand-off to the MMA issuer (leader CTA), one barrier per operand HALF (K blocks 0..3 / 4..7).  Remote mbarrier
+// arrives are slow (~1 us each and they serialise), so the peer CTA joins its 12 operand warps on a named barrier (non-blocking
+// bar.arrive for 11 of them) and warp 0 sends ONE remote arrive; the leader's own warps arrive locally.
+// Leader barrier count = NUM_OPND_WARPS + 1.  Two uses of the same half are always separated by a wait on bar_acc.
+template <int HALF>
+__device__ __forceinline__ void worker_arrive(uint32_t bar_opnd, uint32_t leader_opnd, bool is_leader_cta, int wwarp, int lane) {
     fence_proxy_async();
     tc_fence_before();
     if (is_leader_cta) {
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(bar_local);
+        if (lane == 0) tc::mbar_arrive(bar_opnd + 8 * HALF);
+    } else if (wwarp == 0) {
+        asm volatile("bar.sync %0, %1;" ::"n"(2 + 2 * HALF), "n"(NUM_OPND_WARPS * 32) : "memory");
+        if (lane == 0) mbar_arrive_remote(leader_opnd + 8 * HALF);
     } else {
-        asm volatile("bar.sync 2, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
-        if (wwarp == 0 && lane == 0) mbar_arrive_remote(bar_leader_remote);
+        asm volatile("bar.arrive %0, %1;" ::"n"(2 + 2 * HALF), "n"(NUM_OPND_WARPS * 32) : "memory");
     }
 }
 
@@ -436,16 +438,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     RowTap* taps = (RowTap*)(smem + C::OFF_TAPS);
     const uint32_t bar_full = smem_base + C::OFF_BARS;             // NST: weight stage landed in THIS CTA
     const uint32_t bar_empty = bar_full + 8 * C::NST;              // NST: stage free (pair commit)
-    const uint32_t bar_pfull = bar_empty + 8 * C::NST;             // NST: (leader) peer's stage landed
-    const uint32_t bar_opnd = bar_pfull + 8 * C::NST;              // (leader) A operands of both CTAs ready
-    const uint32_t bar_acc = bar_opnd + 8;                         // accumulators ready / operand buffers free
-    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + C::OFF_BARS + 8 * (3 * C::NST + 2));
+    const uint32_t bar_opnd = bar_empty + 8 * C::NST;              // 2: (leader) A operand half h of both CTAs ready
+    const uint32_t bar_acc = bar_opnd + 16;                        // accumulators of a GEMM step complete (pair commit)
+    const uint32_t bar_afree = bar_acc + 8;                        // 8: K block kb of the A operand no longer read (pair commit)
+    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + C::OFF_BARS + 8 * (2 * C::NST + 3 + HID / KBLK));
 
     if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 90); __trap(); }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); mbar_init(bar_pfull + 8 * i, 1); }
+        for (int i = 0; i < C::NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_opnd, NUM_OPND_WARPS + 1);
+        mbar_init(bar_opnd + 8, NUM_OPND_WARPS + 1);
         mbar_init(bar_acc, 1);
+        for (int i = 0; i < HID / KBLK; ++i) mbar_init(bar_afree + 8 * i, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -457,7 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t leader_opnd = map_to_cta(bar_opnd, 0);
+    const uint32_t leader_opnd = map_to_cta(bar_opnd, 0);      // + 8 * half
 
     // both CTAs of a pair run the same number of rounds; CTA tile = 2 * pair_tile + rank
     const long long first = (long long)blockIdx.x, stride = (long long)gridDim.x;
@@ -471,7 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const bool leader = elect_one();
         const int* table = a.tile_table + (size_t)crank * a.uses_per_tile;
         const uint32_t leader_full = map_to_cta(bar_full, 0);
-        for (long long base = 0; base < ((a.dbg_skip & 16) ? 0 : total_uses); base += C::NST) {
+        for (long long base = 0; base < total_uses; base += C::NST) {
             for (int st = prod_idx; st < C::NST; st += NUM_PRODUCERS) {
                 const long long use = base + st;
                 if (use >= total_uses) break;
@@ -488,22 +492,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             }
         }
     } else if (warp == 1 && is_leader_cta) {
-        // ===== leader CTA: MMA issuer for the pair (converged warp, one elected lane)
+        // ===== leader CTA: MMA issuer for the pair (converged warp, one elected lane).  K-block-outer order: the A operand is
+        //       consumed half by half (K blocks 0..3, then 4..7), each half behind its own operand barrier, and a K block is
+        //       released (bar_afree) right after its last MMA when the step is followed by a gather into the operand buffers.
         const bool leader = elect_one();
-        uint32_t use = 0, it = 0;
+        uint32_t use = 0, oph[2] = {0, 0};
         for (long long rd = 0; rd < n_rounds; ++rd) {
-            for (int sidx = 0; sidx < a.n_steps; ++sidx, ++it) {
+            for (int sidx = 0; sidx < a.n_steps; ++sidx) {
                 const GemmStep gs = a.steps[sidx];
                 const uint32_t idesc = make_idesc2(gs.n_width);
-                if (a.dbg_skip & 64) mbar_poll(bar_opnd, it & 1, a.err, 20); else mbar_wait(bar_opnd, it & 1, a.err, 20);
-                tc_fence_after();
-                TS(0, 2 * sidx);
-                for (int n2 = 0; n2 < gs.n_tiles; ++n2) {
-                    const uint32_t d = tmem + (uint32_t)(gs.dst_col + 128 * n2);
-                    for (int kb = 0; kb < gs.nkb; ++kb) {
+                for (int kb = 0; kb < gs.nkb; ++kb) {
+                    if ((kb & 3) == 0) {
+                        const int h = kb >> 2;
+                        mbar_wait(bar_opnd + 8 * h, oph[h] & 1, a.err, 20 + h);
+                        ++oph[h];
+                        tc_fence_after();
+                        TS(0, 4 * sidx + h);
+                    }
+                    for (int n2 = 0; n2 < gs.n_tiles; ++n2) {
+                        const uint32_t d = tmem + (uint32_t)(gs.dst_col + 128 * n2);
                         {   // W_hi tile: A_hi*W_hi (+ A_lo*W_hi)
                             const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
-                            if (!(a.dbg_skip & 16)) mbar_wait(bar_full + 8 * st, ph, a.err, 30);
+                            mbar_wait(bar_full + 8 * st, ph, a.err, 30);
                             tc_fence_after();
                             if (leader) {
                                 const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
@@ -514,14 +524,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                                     umma2_bf16(d, ahi + 2 * j, bdesc + 2 * j, idesc, (gs.accumulate | kb | j) ? 1u : 0u);
                                     if (PARITY) umma2_bf16(d, alo + 2 * j, bdesc + 2 * j, idesc, 1u);
                                 }
-                                if (!(a.dbg_skip & 16)) umma2_commit_pair(bar_empty + 8 * st);
+                                umma2_commit_pair(bar_empty + 8 * st);
                             }
                             __syncwarp();
                             ++use;
                         }
                         if (PARITY) {   // W_lo tile: A_hi*W_lo
                             const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
-                            if (!(a.dbg_skip & 16)) mbar_wait(bar_full + 8 * st, ph, a.err, 31);
+                            mbar_wait(bar_full + 8 * st, ph, a.err, 31);
                             tc_fence_after();
                             if (leader) {
                                 const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
@@ -534,13 +544,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                             ++use;
                         }
                     }
+                    if (gs.release && leader) umma2_commit_pair(bar_afree + 8 * kb);
+                    __syncwarp();
                 }
                 if (leader) {
-                    if (a.dbg_skip & 32) { tc::mbar_arrive(bar_acc); mbar_arrive_remote(map_to_cta(bar_acc, 1)); }   // experiment: software signal
-                    else umma2_commit_pair(bar_acc);
+                    if (gs.release) for (int kb = gs.nkb; kb < HID / KBLK; ++kb) umma2_commit_pair(bar_afree + 8 * kb);   // K blocks this step never read
+                    umma2_commit_pair(bar_acc);
                 }
                 __syncwarp();
-                TS(0, 2 * sidx + 1);
+                TS(0, 4 * sidx + 2);
             }
         }
     } else if (warp >= WORKER_WARP0) {
@@ -550,7 +562,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const bool helper = wwarp >= NUM_WORKER_WARPS;
         const int q = warp & 3, n2 = (wwarp >> 2) & 1;
         const int r = 32 * (q & 1) + lane;
-        uint32_t it = 0;
+        uint32_t it = 0, gph = 0;
+        (void)gph;
         for (long long rd = 0; rd < n_rounds; ++rd) {
             int tsn = 0; (void)tsn;
             const long long tile_raw = first + rd * stride;
@@ -558,34 +571,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             const long long tile = live ? tile_raw : a.n_tiles - 1;
             if constexpr (KIND == KIND_ZMAP) {
                 // Y_b = W_z[b] . latent for the 64 latent pixels of this tile (once per scene x weights)
+                const bool two_halves = a.steps[0].nkb > 4;
                 load_latent_rows(a, tile, wt, Ahi, Alo);
-                worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                       // -> lin_z[0]
+                worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                    // -> lin_z[0]
+                if (two_halves) worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
                 const long long pix = tile * ROWS + r;
                 for (int b = 0; b < a.n_blocks; ++b) {
                     mbar_wait(bar_acc, it & 1, a.err, 44); ++it;
                     tc_fence_after();
                     if (!helper) store_y_rows(tmem, a.zmap + (size_t)b * a.zmap_stride, pix, live && pix < a.n_pix, q, lane, n2);
                     tc_fence_before();
-                    if (b + 1 < a.n_blocks) worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);           // X free -> lin_z[b+1]
+                    if (b + 1 < a.n_blocks) {                                                                           // X free -> lin_z[b+1]
+                        worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                        if (two_halves) worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    }
                 }
             } else if constexpr (!POST) {
                 if (!(a.dbg_skip & 4)) prep_rows<PARITY>(a, tile, wt, Ahi, Alo, taps);
-                TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> lin_in
+                TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                             // -> lin_in (K block 0 only)
                 for (int b = 0; b < a.n_blocks; ++b) {
-                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 40); else mbar_wait(bar_acc, it & 1, a.err, 40); ++it; TSW();
+                    // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gathered into the operand buffers K block by K block while the
+                    // previous GEMM (lin_in / fc_1[b-1]) is still running, then added to the residual in the epilogue
+                    gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, taps, bar_afree, gph & 1); ++gph;
+                    TSW();
+                    mbar_wait(bar_acc, it & 1, a.err, 40); ++it; TSW();                                                  // x complete
                     tc_fence_after();
-                    // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gather into the (now idle) operand buffers, then add in the epilogue
-                    if (!(a.dbg_skip & 1)) gather_y(a.s, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, taps);
                     asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // staging complete
                     TSW();
-                    if (!helper && !(a.dbg_skip & 2)) epilogue_add_y<PARITY>(tmem, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2);
-                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_0[b]
-                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 42); else mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
+                    if (!helper && !(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2, 0);
+                    TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_0[b], K blocks 0..3
+                    if (!helper && !(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2, 1);
+                    TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_0[b], K blocks 4..7
+                    mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
                     tc_fence_after();
-                    if (!helper && !(a.dbg_skip & 2)) epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + b) * HID, Ahi, Alo, q, lane, n2);
-                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b]
+                    const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
+                    if (!helper && !(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
+                    TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_1[b], K blocks 0..3
+                    if (!helper && !(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
+                    TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_1[b], K blocks 4..7
                 }
-                if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 43); else mbar_wait(bar_acc, it & 1, a.err, 43); ++it; TSW();
+                mbar_wait(bar_acc, it & 1, a.err, 43); ++it; TSW();
                 tc_fence_after();
                 // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
                 const float* cb = a.bias + (size_t)(2 * a.n_blocks) * HID;
@@ -635,18 +660,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         if (PARITY) *(uint4*)(Alo + off) = lo;
                     }
                 }
-                worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> fc_0 of the first post block
+                worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                             // -> fc_0 of the first post block
+                worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
                 for (int b = 0; b < a.n_blocks; ++b) {
-                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 50); else mbar_wait(bar_acc, it & 1, a.err, 50); ++it;
+                    mbar_wait(bar_acc, it & 1, a.err, 50); ++it;
                     tc_fence_after();
-                    if (!helper) epilogue_to_A<PARITY>(tmem, COL_NET, a.bias + (size_t)(a.n_blocks + 1 + b) * HID, Ahi, Alo, q, lane, n2);
-                    TSW(); worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b]
-                    if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 51); else mbar_wait(bar_acc, it & 1, a.err, 51); ++it;
+                    const float* b0 = a.bias + (size_t)(a.n_blocks + 1 + b) * HID;
+                    if (!helper) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
+                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> fc_1[b], K blocks 0..3
+                    if (!helper) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
+                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    mbar_wait(bar_acc, it & 1, a.err, 51); ++it;
                     tc_fence_after();
-                    if (!helper) epilogue_to_A<PARITY>(tmem, COL_X, a.bias + (size_t)(b + 1) * HID, Ahi, Alo, q, lane, n2);
-                    worker_arrive(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> next fc_0 / lin_out
+                    const float* b1 = a.bias + (size_t)(b + 1) * HID;
+                    if (!helper) epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
+                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> next fc_0 / lin_out
+                    if (!helper) epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
+                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
                 }
-                if (a.dbg_skip & 64) mbar_poll(bar_acc, it & 1, a.err, 52); else mbar_wait(bar_acc, it & 1, a.err, 52); ++it;                     // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
+                mbar_wait(bar_acc, it & 1, a.err, 52); ++it;                     // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
                 tc_fence_after();
                 if (!helper && q < 2 && n2 == 0) {
                     uint32_t v[32];
@@ -691,7 +723,7 @@ cudaError_t launch(const Args& a, int grid, cudaStream_t st) {
 
 }  // namespace tc2
 
-// Per-rank weight tile tables of the pair kernel.  Ring-use order of CTA rank r = for each GEMM step, for n2, for kb:
+// Per-rank weight tile tables of the pair kernel.  Ring-use order of CTA rank r = for each GEMM step, for kb, for n2:
 // tile (2*n2 + r) of that layer; every entry is a 16 KiB tile index into the packed stream ([hi][lo] per tile pair).
 // Layout of t.table2: [zmap r0][zmap r1][pre r0][pre r1][post r0][post r1]; zmap is always bf16x3.
 static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cudaStream_t st) {
@@ -702,8 +734,8 @@ static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cu
     auto layer = [&](std::vector<int>* tab, bool par, int nkb, int n_mt, int n_tiles) {
         if (tab)
             for (int r = 0; r < 2; ++r)
-                for (int n2 = 0; n2 < n_tiles; ++n2)
-                    for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb)
+                    for (int n2 = 0; n2 < n_tiles; ++n2) {
                         const int pair = layer_pair0 + (2 * n2 + r) * nkb + kb;
                         tab[r].push_back(2 * pair);
                         if (par) tab[r].push_back(2 * pair + 1);
@@ -765,7 +797,7 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
     z.uses_per_tile = t.uses2_zmap;
     z.bias = t.bias;
     z.n_blocks = t.n_pre;
-    for (int b = 0; b < t.n_pre; ++b) z.steps[b] = GemmStep{(short)(m.d_latent / KBLK), 2, 256, COL_X, 0};
+    for (int b = 0; b < t.n_pre; ++b) z.steps[b] = GemmStep{(short)(m.d_latent / KBLK), 2, 256, COL_X, 0, 0};
     z.n_steps = t.n_pre;
     z.zmap = t.zmap; z.zmap_stride = n_pix * HID; z.n_pix = n_pix;
     z.n_tiles = (n_pix + ROWS - 1) / ROWS;
@@ -818,18 +850,18 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.n_blocks = t.n_pre; post.n_blocks = t.n_post;
     pre.zmap = t.zmap; pre.zmap_stride = (long long)s.SB * s.NV * s.Hl * s.Wl * HID;
     int n = 0;
-    pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0};
+    pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0, 1};                                // lin_in; followed by the gather of Y_0
     for (int b = 0; b < t.n_pre; ++b) {
-        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0};
-        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1};
+        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0};                 // fc_0[b]
+        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, (short)(b + 1 < t.n_pre)};   // fc_1[b]; followed by the gather of Y_{b+1}
     }
     pre.n_steps = n;
     n = 0;
     for (int b = 0; b < t.n_post; ++b) {
-        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0};
-        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1};
+        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0};
+        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 0};
     }
-    post.steps[n++] = GemmStep{(short)kbh, 1, 32, COL_NET, 0};
+    post.steps[n++] = GemmStep{(short)kbh, 1, 32, COL_NET, 0, 0};
     post.n_steps = n;
     pre.NV = post.NV = NV;
     pre.spv = post.spv = ROWS / NV;
@@ -868,11 +900,11 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         for (int cta = 0; cta < 2; ++cta) {
             const long long t0 = pre.dbg_ts[(cta * 4 + 1) * 64];
             fprintf(stderr, "[ts] cta %d worker stamps (arriving, woke, arriving, ...) cycles since first:", cta);
-            for (int i = 0; i < 22; ++i) fprintf(stderr, " %lld", pre.dbg_ts[(cta * 4 + 1) * 64 + i] - t0);
+            for (int i = 0; i < 34; ++i) fprintf(stderr, " %lld", pre.dbg_ts[(cta * 4 + 1) * 64 + i] - t0);
             fprintf(stderr, "\n");
             if (cta == 0) {
-                fprintf(stderr, "[ts] cta 0 mma stamps (opnd-ready, committed per step), same origin:");
-                for (int i = 0; i < 20; ++i) fprintf(stderr, " %lld", pre.dbg_ts[i] - t0);
+                fprintf(stderr, "[ts] cta 0 mma stamps per step (half 0 ready, half 1 ready, committed, -), same origin:");
+                for (int i = 0; i < 28; ++i) fprintf(stderr, " %lld", pre.dbg_ts[i] ? pre.dbg_ts[i] - t0 : 0);
                 fprintf(stderr, "\n");
             }
         }
