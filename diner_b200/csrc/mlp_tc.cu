@@ -688,18 +688,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int out_dim, int
 //   = b_in + sum_{j<=b} b_z[j] + sum_{j<b} b_fc1[j];  rows [n_pre,2n_pre): b_fc0[b];  row 2n_pre: total after the last block.
 // POST (n_post blocks, X starts as the true x_c): row 0 unused (zeros); rows [1,n_post]: sum_{j<=b} b_fc1[pre+j];
 //   rows [n_post+1, 2n_post]: b_fc0[pre+b];  row 2n_post+1: lin_out bias (first 4 entries).
-__global__ void pack_bias_kernel(MlpDev m, float* __restrict__ pre, float* __restrict__ post) {
+// PAIR (pair kernel, lin_z hoisted into the Y maps): rows [0,n_pre): bias folded into Y_b = b_z[b] + (b == 0 ? b_in : b_fc1[b-1]);
+//   row n_pre: b_fc1[n_pre-1], added when the combined x_c is written.
+__global__ void pack_bias_kernel(MlpDev m, float* __restrict__ pre, float* __restrict__ post, float* __restrict__ pair) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= HID) return;
     const int n_pre = m.combine_layer < m.n_blocks ? m.combine_layer : m.n_blocks, n_post = m.n_blocks - n_pre;
     float acc = m.b_in[h];
     for (int b = 0; b < n_pre; ++b) {
+        pair[(size_t)b * HID + h] = m.b_z[b][h] + (b == 0 ? m.b_in[h] : m.b_fc1[b - 1][h]);
         acc += m.b_z[b][h];
         pre[(size_t)b * HID + h] = acc;
         pre[(size_t)(n_pre + b) * HID + h] = m.b_fc0[b][h];
         acc += m.b_fc1[b][h];
     }
     pre[(size_t)(2 * n_pre) * HID + h] = acc;
+    pair[(size_t)n_pre * HID + h] = m.b_fc1[n_pre - 1][h];
     post[h] = 0.0f;
     float acc2 = 0.0f;
     for (int b = 0; b < n_post; ++b) {
@@ -752,7 +756,7 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
         TCK(cudaMalloc(&t.wpack, bytes));
         t.wpack_bytes = bytes;
     }
-    if (!t.bias) TCK(cudaMalloc((void**)&t.bias, (size_t)(4 * DINER_MAX_BLOCKS + 4) * HID * sizeof(float)));
+    if (!t.bias) TCK(cudaMalloc((void**)&t.bias, (size_t)(5 * DINER_MAX_BLOCKS + 6) * HID * sizeof(float)));
     if (!t.err_flag) {   // host-mapped so the watchdog code survives a trapped kernel
         TCK(cudaHostAlloc((void**)&t.err_flag, sizeof(int), cudaHostAllocMapped));
         *t.err_flag = 0;
@@ -776,7 +780,8 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
     }
     TCK(pack(m.w_out, m.d_out, HID, kbh, 2));
     t.bias_post_off = (size_t)(2 * DINER_MAX_BLOCKS + 2) * HID;
-    pack_bias_kernel<<<(HID + 127) / 128, 128, 0, st>>>(m, t.bias, t.bias + t.bias_post_off);
+    t.bias_pair_off = (size_t)(4 * DINER_MAX_BLOCKS + 4) * HID;
+    pack_bias_kernel<<<(HID + 127) / 128, 128, 0, st>>>(m, t.bias, t.bias + t.bias_post_off, t.bias + t.bias_pair_off);
     g_launches++;
     TCK(cudaGetLastError());
     {   // tensor map over the packed stream for the pair kernel's cta_group::2 TMA loads (plain linear 16 KiB boxes)

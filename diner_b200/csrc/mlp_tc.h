@@ -15,7 +15,7 @@ struct TcState {
     int* err_flag = nullptr;      // device-side watchdog flag (mbarrier timeouts)
     int n_pre = 0, n_post = 0;    // ResnetFC blocks before / after the view-combine
     int pairs_pre = 0, pairs_post = 0;   // (hi,lo) weight tile pairs per CTA tile of the PRE / POST kernel
-    size_t bias_post_off = 0;
+    size_t bias_post_off = 0, bias_pair_off = 0;   // float offsets of the POST rows / the pair kernel's folded PRE rows in `bias`
     int cluster = 1;              // thread-block cluster size for weight multicast (1, 2 or 4)
     long long sub_batch = 0;      // samples per PRE/POST launch pair (0 = default)
     int max_grid[3] = {0, 0, 0};

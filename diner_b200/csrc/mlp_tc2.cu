@@ -82,6 +82,7 @@ struct Args {
     const uint8_t* wstream;     // packed weight tiles (16 KiB units), shared with mlp_tc.cu's packing
     const int* tile_table;      // [2][uses_per_tile]: 16 KiB tile index of the i-th ring use of CTA rank r
     const float* bias;
+    const float* bias2;         // pair-kernel PRE rows: [0,n_pre) bias folded into Y_b, row n_pre = b_fc1[n_pre-1] (added at the combine)
     GemmStep steps[MAX_STEPS];
     int n_steps, n_blocks, uses_per_tile;
     long long s_begin, n_samples, n_total, n_tiles;   // n_tiles counts 64-row CTA tiles
@@ -264,34 +265,42 @@ __device__ __forceinline__ void gather_y(const Args& a, const float* __restrict_
         *(float4*)(Ahi + off) = c03;                // channels k0..k0+3
         *(float4*)(Alo + off) = c47;                // channels k0+4..k0+7
     };
+    // Work split: the 8 worker warps take the passes of K blocks 0..5 (released early in the running GEMM), the 4 helper warps
+    // those of K blocks 6..7, which are only released when that GEMM is about to finish -- so that the workers can already run
+    // the first epilogue half while the helpers finish the gather tail.
+    constexpr int WORKER_PASSES = 6 * PASSES_PER_KB;
+    const bool helper = wwarp >= NUM_WORKER_WARPS;
+    const int p_begin = helper ? WORKER_PASSES + (wwarp - NUM_WORKER_WARPS) : wwarp;
+    const int p_end = helper ? n_passes : WORKER_PASSES;
+    const int p_step = helper ? NUM_HELPER_WARPS : NUM_WORKER_WARPS;
     int waited = -1;                                // highest K block whose "free" barrier this warp has passed
 #pragma unroll 1
-    for (int p = wwarp; p < n_passes; p += 2 * NUM_OPND_WARPS) {
+    for (int p = p_begin; p < p_end; p += 2 * p_step) {
         float4 fa[8], fb[8];
         float wa[4], wb[4];
         uint32_t oa, ob = 0;
-        const int p2 = p + NUM_OPND_WARPS;
-        const bool two = p2 < n_passes;
+        const int p2 = p + p_step;
+        const bool two = p2 < p_end;
         const int kb_need = (two ? p2 : p) / PASSES_PER_KB;
-        while (waited < kb_need) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 45); }
+        while (waited < kb_need) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 45); }   // in order: keeps the phase count in step
         issue(p, fa, wa, oa);
         if (two) issue(p2, fb, wb, ob);
         finish(fa, wa, oa);
         if (two) finish(fb, wb, ob);
     }
-    while (waited < HID / KBLK - 1) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 46); }   // keep every warp's phase count in step
+    while (waited < HID / KBLK - 1) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 46); }
 }
 
 // Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row), written back to TMEM as
-// the residual; relu(x' + cumulative bias) -> bf16 hi/lo chunks of the fc_0 operand.  Each thread reads and then overwrites
+// the residual; relu(x') -> bf16 hi/lo chunks of the fc_0 operand.  The biases that precede this point (b_in / b_fc1[b-1] and
+// b_z[b]) are folded into Y_b when the maps are built (the four bilinear weights sum to 1), so the residual in TMEM carries them.  Each thread reads and then overwrites
 // only its own (row, k-chunk) slots, so the staging can live in the operand buffers.
 template <bool PARITY>
-__device__ __forceinline__ void add32_convert(uint32_t* v, const float* __restrict__ bias, int h0, int r, uint8_t* Ahi, uint8_t* Alo) {
+__device__ __forceinline__ void add32_convert(uint32_t* v, int h0, int r, uint8_t* Ahi, uint8_t* Alo) {
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
         const uint32_t off = act_off(r, (h0 >> 3) + c8);
         const float4 g0 = *(const float4*)(Ahi + off), g1 = *(const float4*)(Alo + off);
-        const float4 b0 = __ldg((const float4*)(bias + h0 + 8 * c8)), b1 = __ldg((const float4*)(bias + h0 + 8 * c8 + 4));
         float xs[8], x[8];
         xs[0] = __uint_as_float(v[8 * c8 + 0]) + g0.x; xs[1] = __uint_as_float(v[8 * c8 + 1]) + g0.y;
         xs[2] = __uint_as_float(v[8 * c8 + 2]) + g0.z; xs[3] = __uint_as_float(v[8 * c8 + 3]) + g0.w;
@@ -299,8 +308,8 @@ __device__ __forceinline__ void add32_convert(uint32_t* v, const float* __restri
         xs[6] = __uint_as_float(v[8 * c8 + 6]) + g1.z; xs[7] = __uint_as_float(v[8 * c8 + 7]) + g1.w;
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[8 * c8 + i] = __float_as_uint(xs[i]);
-        x[0] = fmaxf(xs[0] + b0.x, 0.0f); x[1] = fmaxf(xs[1] + b0.y, 0.0f); x[2] = fmaxf(xs[2] + b0.z, 0.0f); x[3] = fmaxf(xs[3] + b0.w, 0.0f);
-        x[4] = fmaxf(xs[4] + b1.x, 0.0f); x[5] = fmaxf(xs[5] + b1.y, 0.0f); x[6] = fmaxf(xs[6] + b1.z, 0.0f); x[7] = fmaxf(xs[7] + b1.w, 0.0f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(xs[i], 0.0f);
         uint4 hi, lo;
         split8(x, hi, lo);
         *(uint4*)(Ahi + off) = hi;
@@ -308,8 +317,7 @@ __device__ __forceinline__ void add32_convert(uint32_t* v, const float* __restri
     }
 }
 template <bool PARITY>
-__device__ __forceinline__ void epilogue_add_y_half(uint32_t tmem, const float* __restrict__ bias, uint8_t* Ahi, uint8_t* Alo, int q,
-                                                    int lane, int j, int h) {
+__device__ __forceinline__ void epilogue_add_y_half(uint32_t tmem, uint8_t* Ahi, uint8_t* Alo, int q, int lane, int j, int h) {
     const int r = 32 * (q & 1) + lane;
     const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * h + 64 * j);
     const int hb = 256 * h + 128 * (q >> 1) + 64 * j;
@@ -317,9 +325,9 @@ __device__ __forceinline__ void epilogue_add_y_half(uint32_t tmem, const float* 
     tmem_ld32_issue(t0, va);
     tmem_ld32_issue(t0 + 32, vb);
     tmem_ld_wait();
-    add32_convert<PARITY>(va, bias, hb, r, Ahi, Alo);
+    add32_convert<PARITY>(va, hb, r, Ahi, Alo);
     tmem_st32_issue(t0, va);
-    add32_convert<PARITY>(vb, bias, hb + 32, r, Ahi, Alo);
+    add32_convert<PARITY>(vb, hb + 32, r, Ahi, Alo);
     tmem_st32_issue(t0 + 32, vb);
     tmem_st_wait();
 }
@@ -343,7 +351,8 @@ __device__ __forceinline__ void load_latent_rows(const Args& a, long long tile, 
     }
 }
 // ZMAP: accumulator rows -> Y_b[pixel][512] fp32 (thread = row, 128 contiguous bytes per TMEM load)
-__device__ __forceinline__ void store_y_rows(uint32_t tmem, float* __restrict__ ymap, long long pix, bool write, int q, int lane, int n2) {
+__device__ __forceinline__ void store_y_rows(uint32_t tmem, float* __restrict__ ymap, const float* __restrict__ bias, long long pix, bool write,
+                                             int q, int lane, int n2) {
     const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2);
     const int hb = 256 * n2 + 128 * (q >> 1);
 #pragma unroll 1
@@ -352,9 +361,13 @@ __device__ __forceinline__ void store_y_rows(uint32_t tmem, float* __restrict__ 
         tmem_ld32(t0 + 32 * c32, v);
         if (write) {
             float4* dst = (float4*)(ymap + (size_t)pix * HID + hb + 32 * c32);
+            const float4* bs = (const float4*)(bias + hb + 32 * c32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            for (int i = 0; i < 8; ++i) {
+                const float4 bv = __ldg(bs + i);
+                dst[i] = make_float4(__uint_as_float(v[4 * i]) + bv.x, __uint_as_float(v[4 * i + 1]) + bv.y, __uint_as_float(v[4 * i + 2]) + bv.z,
+                                     __uint_as_float(v[4 * i + 3]) + bv.w);
+            }
         }
     }
 }
@@ -401,10 +414,11 @@ __device__ __forceinline__ void combine_store(uint32_t* raw, const float* __rest
     }
 }
 
-// Operand hand-off to the MMA issuer (leader CTA), one barrier per operand HALF (K blocks 0..3 / 4..7).  Remote mbarrier
-// arrives are slow (~1 us each and they serialise), so the peer CTA joins its 12 operand warps on a named barrier (non-blocking
-// bar.arrive for 11 of them) and warp 0 sends ONE remote arrive; the leader's own warps arrive locally.
-// Leader barrier count = NUM_OPND_WARPS + 1.  Two uses of the same half are always separated by a wait on bar_acc.
+// Operand hand-off to the MMA issuer (leader CTA), one barrier per operand HALF (K blocks 0..3 / 4..7); called by the 8 WORKER
+// warps only (helper warps hand their prep / gather results to the workers through named barriers).  Remote mbarrier arrives
+// are slow (~1 us each and they serialise), so the peer CTA joins its worker warps on a named barrier (non-blocking bar.arrive
+// for 7 of them) and warp 0 sends ONE remote arrive; the leader's own warps arrive locally.  Leader barrier count =
+// NUM_WORKER_WARPS + 1.  Two uses of the same half are always separated by a wait on bar_acc.
 template <int HALF>
 __device__ __forceinline__ void worker_arrive(uint32_t bar_opnd, uint32_t leader_opnd, bool is_leader_cta, int wwarp, int lane) {
     fence_proxy_async();
@@ -413,15 +427,21 @@ __device__ __forceinline__ void worker_arrive(uint32_t bar_opnd, uint32_t leader
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(bar_opnd + 8 * HALF);
     } else if (wwarp == 0) {
-        asm volatile("bar.sync %0, %1;" ::"n"(2 + 2 * HALF), "n"(NUM_OPND_WARPS * 32) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(2 + 2 * HALF), "n"(NUM_WORKERS) : "memory");
         if (lane == 0) mbar_arrive_remote(leader_opnd + 8 * HALF);
     } else {
-        asm volatile("bar.arrive %0, %1;" ::"n"(2 + 2 * HALF), "n"(NUM_OPND_WARPS * 32) : "memory");
+        asm volatile("bar.arrive %0, %1;" ::"n"(2 + 2 * HALF), "n"(NUM_WORKERS) : "memory");
     }
 }
+// all 12 operand warps (prep / operand loads that the helpers take part in): generic-proxy writes -> async proxy, then join
+__device__ __forceinline__ void opnd_warps_join() {
+    fence_proxy_async();
+    asm volatile("bar.sync 6, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+}
 
-#define TS(role, slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == 1 && lane == 0) a.dbg_ts[(blockIdx.x * 4 + (role)) * 64 + (slot)] = clock64(); } while (0)
-#define TSW() do { if (a.dbg_ts && blockIdx.x < 2 && rd == 1 && wwarp == 0 && lane == 0 && tsn < 64) a.dbg_ts[(blockIdx.x * 4 + 1) * 64 + tsn++] = clock64(); } while (0)
+#define TS_ROUND 20     // a steady-state round (the first rounds of a launch gather cold Y-map lines from HBM)
+#define TS(role, slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && lane == 0) a.dbg_ts[(blockIdx.x * 4 + (role)) * 64 + (slot)] = clock64(); } while (0)
+#define TSW() do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && wwarp == 0 && lane == 0 && tsn < 64) a.dbg_ts[(blockIdx.x * 4 + 1) * 64 + tsn++] = clock64(); } while (0)
 // ---- the kernel ----------------------------------------------------------------------------------
 constexpr int KIND_PRE = 0, KIND_POST = 1, KIND_ZMAP = 2;
 template <bool PARITY, int KIND>
@@ -446,8 +466,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 90); __trap(); }
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-        mbar_init(bar_opnd, NUM_OPND_WARPS + 1);
-        mbar_init(bar_opnd + 8, NUM_OPND_WARPS + 1);
+        mbar_init(bar_opnd, NUM_WORKER_WARPS + 1);
+        mbar_init(bar_opnd + 8, NUM_WORKER_WARPS + 1);
         mbar_init(bar_acc, 1);
         for (int i = 0; i < HID / KBLK; ++i) mbar_init(bar_afree + 8 * i, 1);
         fence_barrier_init();
@@ -573,22 +593,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 // Y_b = W_z[b] . latent for the 64 latent pixels of this tile (once per scene x weights)
                 const bool two_halves = a.steps[0].nkb > 4;
                 load_latent_rows(a, tile, wt, Ahi, Alo);
-                worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                    // -> lin_z[0]
-                if (two_halves) worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                opnd_warps_join();
+                if (!helper) {                                                                                          // -> lin_z[0]
+                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    if (two_halves) worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                }
                 const long long pix = tile * ROWS + r;
                 for (int b = 0; b < a.n_blocks; ++b) {
                     mbar_wait(bar_acc, it & 1, a.err, 44); ++it;
                     tc_fence_after();
-                    if (!helper) store_y_rows(tmem, a.zmap + (size_t)b * a.zmap_stride, pix, live && pix < a.n_pix, q, lane, n2);
-                    tc_fence_before();
-                    if (b + 1 < a.n_blocks) {                                                                           // X free -> lin_z[b+1]
-                        worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                        if (two_halves) worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    if (!helper) {
+                        store_y_rows(tmem, a.zmap + (size_t)b * a.zmap_stride, a.bias2 + (size_t)b * HID, pix, live && pix < a.n_pix, q, lane, n2);
+                        tc_fence_before();
+                        if (b + 1 < a.n_blocks) {                                                                       // X free -> lin_z[b+1]
+                            worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                            if (two_halves) worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                        }
                     }
                 }
             } else if constexpr (!POST) {
                 if (!(a.dbg_skip & 4)) prep_rows<PARITY>(a, tile, wt, Ahi, Alo, taps);
-                TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                             // -> lin_in (K block 0 only)
+                opnd_warps_join();
+                TSW();
+                if (!helper) worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                       // -> lin_in (K block 0 only)
                 for (int b = 0; b < a.n_blocks; ++b) {
                     // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gathered into the operand buffers K block by K block while the
                     // previous GEMM (lin_in / fc_1[b-1]) is still running, then added to the residual in the epilogue
@@ -596,24 +623,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     TSW();
                     mbar_wait(bar_acc, it & 1, a.err, 40); ++it; TSW();                                                  // x complete
                     tc_fence_after();
-                    asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // staging complete
-                    TSW();
-                    if (!helper && !(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2, 0);
-                    TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_0[b], K blocks 0..3
-                    if (!helper && !(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, a.bias + (size_t)b * HID, Ahi, Alo, q, lane, n2, 1);
-                    TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_0[b], K blocks 4..7
+                    if (helper) {
+                        asm volatile("bar.arrive 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                        // staging of K blocks 6..7 complete
+                    } else {
+                        asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..5 complete
+                        if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 0);
+                        TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 0..3
+                        asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                        if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 1);
+                        TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 4..7
+                    }
                     mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
                     tc_fence_after();
-                    const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
-                    if (!helper && !(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
-                    TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_1[b], K blocks 0..3
-                    if (!helper && !(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
-                    TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                         // -> fc_1[b], K blocks 4..7
+                    if (!helper) {
+                        const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
+                        if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
+                        TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 0..3
+                        if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
+                        TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 4..7
+                    }
                 }
                 mbar_wait(bar_acc, it & 1, a.err, 43); ++it; TSW();
                 tc_fence_after();
                 // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
-                const float* cb = a.bias + (size_t)(2 * a.n_blocks) * HID;
+                const float* cb = a.bias2 + (size_t)a.n_blocks * HID;                // b_fc1 of the last block (everything earlier is in x already)
                 const long long smp = tile * a.spv + r / a.NV;                   // sample within the sub-batch
                 const bool wr = live && smp < a.n_samples;
                 float* dst_sample = a.xc + (size_t)(wr ? smp : 0) * HID;
@@ -660,23 +693,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         if (PARITY) *(uint4*)(Alo + off) = lo;
                     }
                 }
-                worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                             // -> fc_0 of the first post block
-                worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                if (!helper) {                                                                                          // -> fc_0 of the first post block
+                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                }
                 for (int b = 0; b < a.n_blocks; ++b) {
                     mbar_wait(bar_acc, it & 1, a.err, 50); ++it;
                     tc_fence_after();
-                    const float* b0 = a.bias + (size_t)(a.n_blocks + 1 + b) * HID;
-                    if (!helper) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
-                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> fc_1[b], K blocks 0..3
-                    if (!helper) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
-                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    if (!helper) {
+                        const float* b0 = a.bias + (size_t)(a.n_blocks + 1 + b) * HID;
+                        epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
+                        worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b], K blocks 0..3
+                        epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
+                        worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    }
                     mbar_wait(bar_acc, it & 1, a.err, 51); ++it;
                     tc_fence_after();
-                    const float* b1 = a.bias + (size_t)(b + 1) * HID;
-                    if (!helper) epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
-                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // -> next fc_0 / lin_out
-                    if (!helper) epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
-                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    if (!helper) {
+                        const float* b1 = a.bias + (size_t)(b + 1) * HID;
+                        epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
+                        worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> next fc_0 / lin_out
+                        epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
+                        worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    }
                 }
                 mbar_wait(bar_acc, it & 1, a.err, 52); ++it;                     // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
                 tc_fence_after();
@@ -795,7 +834,7 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
     z.wstream = (const uint8_t*)t.wpack;
     z.tile_table = t.table2;
     z.uses_per_tile = t.uses2_zmap;
-    z.bias = t.bias;
+    z.bias = t.bias; z.bias2 = t.bias + t.bias_pair_off;
     z.n_blocks = t.n_pre;
     for (int b = 0; b < t.n_pre; ++b) z.steps[b] = GemmStep{(short)(m.d_latent / KBLK), 2, 256, COL_X, 0, 0};
     z.n_steps = t.n_pre;
@@ -847,6 +886,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.tile_table = t.table2 + 2 * t.uses2_zmap; post.tile_table = pre.tile_table + 2 * t.uses2_pre;
     pre.uses_per_tile = t.uses2_pre; post.uses_per_tile = t.uses2_post;
     pre.bias = t.bias; post.bias = t.bias + t.bias_post_off;
+    pre.bias2 = post.bias2 = t.bias + t.bias_pair_off;
     pre.n_blocks = t.n_pre; post.n_blocks = t.n_post;
     pre.zmap = t.zmap; pre.zmap_stride = (long long)s.SB * s.NV * s.Hl * s.Wl * HID;
     int n = 0;
