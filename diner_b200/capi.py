@@ -34,6 +34,8 @@ SIGNATURES = {
     "diner_set_mlp": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _PP, _PP, _PP, _PP, _PP, _PP, _P]),
     "diner_set_scene": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _P]),
     "diner_render": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P, _P, _P]),
+    "diner_render_image": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
+    "diner_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P]),
     "diner_render_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _U64, _P, _P, _P]),
     "diner_sample": (_I, [_P, _P, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
     "diner_query": (_I, [_P, _P, _P, _I, _LL, _I, _P, _P]),
@@ -180,6 +182,33 @@ class Context:
                 ctypes.byref(n) if n is not None else None, _ptr(rgb), _ptr(depth), _ptr(w), _ptr(z),
                 _stream(self.device)))
         return rgb, depth, w, z
+
+    def render_image(self, target_extrinsics, target_intrinsics, H, W, z_near, z_far, K, C, G, white_bkgd, mode, noise=None):
+        """gen_rays + the ray-batch loop of DINER.predict_imgs_from_batch (diner.py:79-92) in one library call.
+        Returns rgb (SB,H*W,3), depth (SB,H*W); noise may only carry a seed (dense noise is per ray batch)."""
+        SB = target_extrinsics.shape[0]
+        dev = target_extrinsics.device
+        rgb = torch.empty(SB, H * W, 3, device=dev)
+        depth = torch.empty(SB, H * W, device=dev)
+        n, keep = self._noise(noise, SB, H * W, K, C, G)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.diner_render_image(
+                self.handle, _ptr(target_extrinsics, (SB, 4, 4), "target_extrinsics"),
+                _ptr(target_intrinsics, (SB, 3, 3), "target_intrinsics"), SB, H, W, float(z_near), float(z_far), K, C, G,
+                int(bool(white_bkgd)), mode, ctypes.byref(n) if n is not None else None, _ptr(rgb), _ptr(depth),
+                _stream(self.device)))
+        return rgb, depth
+
+    def gen_rays(self, target_extrinsics, target_intrinsics, H, W, z_near, z_far):
+        """src/util/cam_geometry.py:5-48 on the device: (SB,H*W,8)."""
+        SB = target_extrinsics.shape[0]
+        rays = torch.empty(SB, H * W, 8, device=target_extrinsics.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.diner_gen_rays(
+                self.handle, _ptr(target_extrinsics, (SB, 4, 4), "target_extrinsics"),
+                _ptr(target_intrinsics, (SB, 3, 3), "target_intrinsics"), SB, H, W, float(z_near), float(z_far),
+                _ptr(rays), _stream(self.device)))
+        return rays
 
     def sample(self, rays, K, C, G, noise=None, want_dgs=False):
         SB, NR, _ = rays.shape

@@ -50,7 +50,7 @@ struct diner_ctx {
     DevBuf mlp_store;                // all fp32 parameters, contiguous
     SceneDev scene{};
     DevBuf latent, maps, cams;       // library-owned scene copies
-    DevBuf zbuf, netbuf, simt_ws, rays_dev, out_dev;
+    DevBuf zbuf, netbuf, simt_ws, rays_dev, out_dev, rays_img;
     void* host_pin = nullptr; size_t host_pin_cap = 0;
     TcState tc;                      // packed weights + scratch of the tcgen05 path
     long long launches = 0;
@@ -90,7 +90,7 @@ extern "C" void diner_destroy(diner_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     c->mlp_store.release(); c->latent.release(); c->maps.release(); c->cams.release();
-    c->zbuf.release(); c->netbuf.release(); c->simt_ws.release(); c->rays_dev.release(); c->out_dev.release();
+    c->zbuf.release(); c->netbuf.release(); c->simt_ws.release(); c->rays_dev.release(); c->out_dev.release(); c->rays_img.release();
     tc_release(c->tc);
     if (c->host_pin) cudaFreeHost(c->host_pin);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -358,6 +358,30 @@ extern "C" int diner_render(diner_ctx* c, const float* rays, int SB, int NR, int
     if (!rc) rc = do_composite(c, rays, zz, SB, NR, K, white_bkgd, mode, rgb, depth, weights, st);
     c->launches += g_launches - l0;
     return rc;
+}
+
+extern "C" int diner_gen_rays(diner_ctx* c, const float* target_extrinsics, const float* target_intrinsics, int SB, int H, int W,
+                              float z_near, float z_far, float* rays, void* stream) {
+    if (!c) return fail(DINER_E_INVALID, "ctx is NULL");
+    if (SB < 1 || H < 1 || W < 1) return fail(DINER_E_INVALID, "bad SB=%d H=%d W=%d", SB, H, W);
+    if (!target_extrinsics || !target_intrinsics || !rays) return fail(DINER_E_INVALID, "NULL pointer argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(launch_gen_rays(target_extrinsics, target_intrinsics, SB, H, W, z_near, z_far, rays, c->num_sms, (cudaStream_t)stream));
+    g_launches++; c->launches++;
+    return DINER_OK;
+}
+
+extern "C" int diner_render_image(diner_ctx* c, const float* target_extrinsics, const float* target_intrinsics, int SB, int H, int W,
+                                  float z_near, float z_far, int K, int C, int G, int white_bkgd, int mode,
+                                  const diner_noise* noise, float* rgb, float* depth, void* stream) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (H < 1 || W < 1 || (long long)H * W > 0x7fffffffLL) return fail(DINER_E_INVALID, "bad image size %dx%d", W, H);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->rays_img.reserve((size_t)SB * H * W * 8 * sizeof(float)));
+    rc = diner_gen_rays(c, target_extrinsics, target_intrinsics, SB, H, W, z_near, z_far, c->rays_img.as<float>(), stream);
+    if (rc) return rc;
+    return diner_render(c, c->rays_img.as<float>(), SB, H * W, K, C, G, white_bkgd, mode, noise, rgb, depth, nullptr, nullptr, stream);
 }
 
 extern "C" int diner_render_host(diner_ctx* c, const float* rays_host, int SB, int NR, int K, int C, int G,

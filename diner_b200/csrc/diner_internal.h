@@ -58,5 +58,7 @@ cudaError_t launch_composite(const float* rays, const float* z, const float* net
 
 // --- scene re-layout (scene.cu) ---------------------------------------------------------------------
 cudaError_t launch_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, cudaStream_t st);
+cudaError_t launch_gen_rays(const float* ext, const float* intr, int SB, int H, int W, float z_near, float z_far, float* rays,
+                            int num_sms, cudaStream_t st);
 cudaError_t upload_std_ring_gain();
 extern long long g_launches;   // bumped at every kernel launch site

@@ -48,7 +48,7 @@ constexpr int B_BYTES = HID * TILE_N * 2;   // 64 KiB per bf16 copy of the B ope
 constexpr int TMEM_COLS = 512;
 constexpr int COL_X = 0, COL_NET = 256;
 constexpr int MAX_STEPS = 3 * DINER_MAX_BLOCKS + 2;
-constexpr uint32_t SPIN_LIMIT = 1u << 27;
+constexpr uint32_t SPIN_LIMIT = 1u << 23;   // a protocol bug traps within a fraction of a second instead of hanging the box
 
 struct GemmStep {
     short nkb;        // K blocks of 64

@@ -26,7 +26,6 @@
 
 namespace tc2 {
 
-using tc::RowTap;
 using tc::smem_u32;
 using tc::mbar_init;
 using tc::mbar_arrive_expect_tx;
@@ -66,13 +65,21 @@ constexpr int TMEM_COLS = 512;
 constexpr int COL_X = 0, COL_NET = 256;
 constexpr int MAX_STEPS = 3 * DINER_MAX_BLOCKS + 2;
 
+// Bilinear tap set of one sample-view row (16 B, double-buffered: the helper warps compute the next tile's taps during the
+// current tile's last block).  ex = 1 - wx and ey = 1 - wy bit-exactly equal image_encoder's (x0 + 1) - x: x - floor(x) is exact.
+struct Tap {
+    int pix_dxy;       // pixel index of tap (0,0) (view base included) | dx << 30 | dy << 31 (dx/dy = 0 when clamped at the border)
+    float wx, wy;
+    int pad;
+};
+
 struct GemmStep {
     short nkb;         // K blocks of 64
     short n_tiles;     // N tiles (of n_width hidden units) = weight tiles per CTA per K block
     short n_width;     // UMMA N: 256, or 32 for lin_out
     short dst_col;     // TMEM column base
     short accumulate;
-    short release;     // commit the per-K-block "A operand free" barriers (the step is followed by a gather into A)
+    short release;     // commit the per-K-block "A operand free" barriers (a gather into A overlaps / follows the step); 2 = lin_in
 };
 
 struct Args {
@@ -143,7 +150,7 @@ template <bool PARITY> struct Cfg {
     static constexpr int OFF_A_HI = NST * WTILE_BYTES;
     static constexpr int OFF_A_LO = OFF_A_HI + ACT_BYTES;
     static constexpr int OFF_TAPS = OFF_A_LO + ACT_BYTES;
-    static constexpr int OFF_BARS = OFF_TAPS + ROWS * (int)sizeof(RowTap);
+    static constexpr int OFF_BARS = OFF_TAPS + 2 * ROWS * (int)sizeof(Tap);
     static constexpr int SMEM_BYTES = OFF_BARS + 256;
 };
 
@@ -185,12 +192,12 @@ __device__ __forceinline__ void epilogue_half(uint32_t tmem, int colbase, const 
     convert32<PARITY>(vb, bias, hb + 32, r, Ahi, Alo);
 }
 
-// PRE prep: 4 threads per row -> lin_in A operand (K block 0) + bilinear tap set
-template <bool PARITY>
-__device__ __forceinline__ void prep_rows(const Args& a, long long tile, int wt, uint8_t* Ahi, uint8_t* Alo, RowTap* taps) {
+// PRE prep: PARTS threads per row (wt = row + 64 * part).  Camera transform, projection, nearest depth; TAPS: the row's
+// bilinear tap set for the Y-map gathers; FEAT: positional encodings etc. -> the lin_in A operand (K block 0).
+template <bool PARITY, int PARTS, bool TAPS, bool FEAT>
+__device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, uint8_t* Ahi, uint8_t* Alo, Tap* taps) {
     const SceneDev& s = a.s;
-    const int r = wt & 63, part = wt >> 6;            // NUM_OPND_WARPS * 32 / 64 threads per row
-    constexpr int PARTS = NUM_OPND_WARPS * 32 / 64;
+    const int r = wt & 63, part = wt >> 6;
     long long smp = a.s_begin + tile * a.spv + r / a.NV;
     if (smp >= a.n_total) smp = a.n_total - 1;
     const int v = r % a.NV;
@@ -204,52 +211,59 @@ __device__ __forceinline__ void prep_rows(const Args& a, long long tile, int wt,
     for (int k = 0; k < 12; ++k) p[k] = __ldg(P + k);
     float xc, yc, zc, dxc, dyc, dzc;
     world_to_cam(p, px, py, pz, xc, yc, zc);
-    rotate_to_cam(p, dx, dy, dz, dxc, dyc, dzc);
     const float u = project_axis(xc, zc, __ldg(s.focal + sv * 2), __ldg(s.cxy + sv * 2), s.imgW);
     const float w = project_axis(yc, zc, __ldg(s.focal + sv * 2 + 1), __ldg(s.cxy + sv * 2 + 1), s.imgH);
-    const float dd = __fsub_rn(lookup_depth(s, sv, u, w), zc);
-    if (part == 0) {
+    if (TAPS && part == 0) {
         const LatTaps t = latent_taps(s, u, w);
-        RowTap rt;
-        rt.pix00 = sv * s.Hl * s.Wl + t.o00;
-        rt.dxy = (t.o01 != t.o00 ? 1 : 0) | (t.o10 != t.o00 ? 2 : 0);
+        Tap rt;
+        rt.pix_dxy = (sv * s.Hl * s.Wl + t.o00) | (t.o01 != t.o00 ? (1 << 30) : 0) | (t.o10 != t.o00 ? (int)(1u << 31) : 0);
         float x = unnormalize(__fmul_rn(u, s.lat_sx), (float)s.Wl), y = unnormalize(__fmul_rn(w, s.lat_sy), (float)s.Hl);
         x = fminf(fmaxf(x, 0.0f), (float)(s.Wl - 1));
         y = fminf(fmaxf(y, 0.0f), (float)(s.Hl - 1));
         if (!(x == x)) x = 0.0f;
         if (!(y == y)) y = 0.0f;
-        const float xf = floorf(x), yf = floorf(y);
-        rt.ex = (xf + 1.0f) - x; rt.wx = x - xf; rt.ey = (yf + 1.0f) - y; rt.wy = y - yf;
+        rt.wx = x - floorf(x); rt.wy = y - floorf(y);
+        rt.pad = 0;
         taps[r] = rt;
     }
-    const int d_in = 3 + 6 * s.num_freqs + 3 + 1 + 2 * s.num_freqs;
+    if (FEAT) {
+        rotate_to_cam(p, dx, dy, dz, dxc, dyc, dzc);
+        const float dd = __fsub_rn(lookup_depth(s, sv, u, w), zc);
+        const int d_in = 3 + 6 * s.num_freqs + 3 + 1 + 2 * s.num_freqs;
 #pragma unroll 1
-    for (int e = part; e < KBLK; e += PARTS) {
-        const float val = e < d_in ? feature_elem(e, s.num_freqs, s.freqs, xc, yc, zc, dxc, dyc, dzc, dd) : 0.0f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-        const uint32_t off = act_off(r, e >> 3) + (uint32_t)(e & 7) * 2u;
-        *(__nv_bfloat16*)(Ahi + off) = hi;
-        if (PARITY) *(__nv_bfloat16*)(Alo + off) = __float2bfloat16_rn(val - __bfloat162float(hi));
+        for (int e = part; e < KBLK; e += PARTS) {
+            const float val = e < d_in ? feature_elem(e, s.num_freqs, s.freqs, xc, yc, zc, dxc, dyc, dzc, dd) : 0.0f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+            const uint32_t off = act_off(r, e >> 3) + (uint32_t)(e & 7) * 2u;
+            *(__nv_bfloat16*)(Ahi + off) = hi;
+            if (PARITY) *(__nv_bfloat16*)(Alo + off) = __float2bfloat16_rn(val - __bfloat162float(hi));
+        }
     }
 }
 
-// PRE gather: bilinear Y_b (= lin_z[b] of the latent map) rows of this tile -> fp32 staging in the (A_hi, A_lo) chunk slots,
-// in K-BLOCK ORDER and overlapped with the GEMM that is still reading the operand buffers: before touching K block kb the warp
-// waits on bar_afree[kb], which the MMA issuer commits right after the last MMA that reads that K block.
+// PRE gather: bilinear Y_b (= lin_z[b] of the latent map) rows of a tile -> fp32 staging in the (A_hi, A_lo) chunk slots, for
+// the K blocks [kb_lo, kb_hi], in K-BLOCK ORDER and overlapped with the GEMM that is still reading the operand buffers: before
+// touching K block kb the warp waits on bar_afree[kb], which the MMA issuer commits right after the last MMA that reads it.
+// Every warp waits on every barrier of the range, in order (keeps the phase parities in step): par0 is the parity of
+// bar_afree[0], par1 that of the others (K block 0 has one more release per tile: it also carries the lin_in features).
 // One pass = 4 rows x 64 channels (one K block): lane -> row 4*(p%16) + lane/8, 8 channels (lane%8): 32-byte loads per tap;
 // channels 0..3 of the chunk go to the hi slot, 4..7 to the lo slot (the epilogue thread that owns the row reads them back).
-__device__ __forceinline__ void gather_y(const Args& a, const float* __restrict__ ymap, int wwarp, int lane, uint8_t* Ahi,
-                                         uint8_t* Alo, const RowTap* taps, uint32_t bar_afree, uint32_t parity) {
+// Work split: the 8 worker warps take K blocks <= 4 (released early in the running GEMM), the 4 helper warps K blocks 5..7,
+// which are released when that GEMM is about to finish -- the workers run the first epilogue half meanwhile.
+__device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ ymap, int wwarp, int lane, uint8_t* Ahi,
+                                         uint8_t* Alo, const Tap* taps, int kb_lo, int kb_hi, uint32_t bar_afree, uint32_t par0,
+                                         uint32_t par1) {
     const SceneDev& s = a.s;
     constexpr int PASSES_PER_KB = ROWS / 4;         // 16
-    constexpr int n_passes = PASSES_PER_KB * (HID / KBLK);   // 128
+    constexpr int WORKER_KB_HI = 4;
     auto issue = [&](int p, float4 (&f)[8], float (&w)[4], uint32_t& off) {
         const int kb = p / PASSES_PER_KB, r = 4 * (p % PASSES_PER_KB) + (lane >> 3);
-        const RowTap rt = taps[r];
-        const size_t ox = (rt.dxy & 1) ? (size_t)HID : 0, oy = (rt.dxy & 2) ? (size_t)s.Wl * HID : 0;
-        w[0] = rt.ex * rt.ey; w[1] = rt.wx * rt.ey; w[2] = rt.ex * rt.wy; w[3] = rt.wx * rt.wy;
+        const Tap rt = taps[r];
+        const size_t ox = (rt.pix_dxy & (1 << 30)) ? (size_t)HID : 0, oy = (rt.pix_dxy < 0) ? (size_t)s.Wl * HID : 0;
+        const float ex = 1.0f - rt.wx, ey = 1.0f - rt.wy;
+        w[0] = ex * ey; w[1] = rt.wx * ey; w[2] = ex * rt.wy; w[3] = rt.wx * rt.wy;
         const int k0 = KBLK * kb + 8 * (lane & 7);
-        const float* b00 = ymap + (size_t)rt.pix00 * HID + k0;
+        const float* b00 = ymap + (size_t)(rt.pix_dxy & 0x3FFFFFFF) * HID + k0;
         f[0] = __ldg((const float4*)b00); f[1] = __ldg((const float4*)(b00 + 4));
         f[2] = __ldg((const float4*)(b00 + ox)); f[3] = __ldg((const float4*)(b00 + ox + 4));
         f[4] = __ldg((const float4*)(b00 + oy)); f[5] = __ldg((const float4*)(b00 + oy + 4));
@@ -265,15 +279,13 @@ __device__ __forceinline__ void gather_y(const Args& a, const float* __restrict_
         *(float4*)(Ahi + off) = c03;                // channels k0..k0+3
         *(float4*)(Alo + off) = c47;                // channels k0+4..k0+7
     };
-    // Work split: the 8 worker warps take the passes of K blocks 0..5 (released early in the running GEMM), the 4 helper warps
-    // those of K blocks 6..7, which are only released when that GEMM is about to finish -- so that the workers can already run
-    // the first epilogue half while the helpers finish the gather tail.
-    constexpr int WORKER_PASSES = 6 * PASSES_PER_KB;
     const bool helper = wwarp >= NUM_WORKER_WARPS;
-    const int p_begin = helper ? WORKER_PASSES + (wwarp - NUM_WORKER_WARPS) : wwarp;
-    const int p_end = helper ? n_passes : WORKER_PASSES;
+    const int my_lo = helper ? (kb_lo > WORKER_KB_HI + 1 ? kb_lo : WORKER_KB_HI + 1) : kb_lo;
+    const int my_hi = helper ? kb_hi : (kb_hi < WORKER_KB_HI ? kb_hi : WORKER_KB_HI);
     const int p_step = helper ? NUM_HELPER_WARPS : NUM_WORKER_WARPS;
-    int waited = -1;                                // highest K block whose "free" barrier this warp has passed
+    const int p_begin = my_lo * PASSES_PER_KB + (helper ? wwarp - NUM_WORKER_WARPS : wwarp);
+    const int p_end = (my_hi + 1) * PASSES_PER_KB;   // <= p_begin when this warp class has no K block in the range
+    int waited = kb_lo - 1;                         // highest K block whose "free" barrier this warp has passed
 #pragma unroll 1
     for (int p = p_begin; p < p_end; p += 2 * p_step) {
         float4 fa[8], fb[8];
@@ -282,13 +294,13 @@ __device__ __forceinline__ void gather_y(const Args& a, const float* __restrict_
         const int p2 = p + p_step;
         const bool two = p2 < p_end;
         const int kb_need = (two ? p2 : p) / PASSES_PER_KB;
-        while (waited < kb_need) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 45); }   // in order: keeps the phase count in step
+        while (waited < kb_need) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 45); }
         issue(p, fa, wa, oa);
         if (two) issue(p2, fb, wb, ob);
         finish(fa, wa, oa);
         if (two) finish(fb, wb, ob);
     }
-    while (waited < HID / KBLK - 1) { ++waited; mbar_wait(bar_afree + 8 * waited, parity, a.err, 46); }
+    while (waited < kb_hi) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 46); }
 }
 
 // Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row), written back to TMEM as
@@ -455,7 +467,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     const uint32_t smem_base = smem_u32(smem);
     uint8_t* Ahi = smem + C::OFF_A_HI;
     uint8_t* Alo = smem + C::OFF_A_LO;
-    RowTap* taps = (RowTap*)(smem + C::OFF_TAPS);
+    Tap* taps = (Tap*)(smem + C::OFF_TAPS);                        // [2][ROWS]
     const uint32_t bar_full = smem_base + C::OFF_BARS;             // NST: weight stage landed in THIS CTA
     const uint32_t bar_empty = bar_full + 8 * C::NST;              // NST: stage free (pair commit)
     const uint32_t bar_opnd = bar_empty + 8 * C::NST;              // 2: (leader) A operand half h of both CTAs ready
@@ -568,7 +580,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     __syncwarp();
                 }
                 if (leader) {
-                    if (gs.release) for (int kb = gs.nkb; kb < HID / KBLK; ++kb) umma2_commit_pair(bar_afree + 8 * kb);   // K blocks this step never read
+                    // lin_in (release == 2) reads K block 0 only; in the first round the gather of the whole Y_0 row set follows it, so
+                    // the other K blocks are released here as well (later rounds gather them during the previous tile's last fc_1)
+                    if (gs.release == 2 && rd == 0) for (int kb = gs.nkb; kb < HID / KBLK; ++kb) umma2_commit_pair(bar_afree + 8 * kb);
                     umma2_commit_pair(bar_acc);
                 }
                 __syncwarp();
@@ -582,8 +596,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const bool helper = wwarp >= NUM_WORKER_WARPS;
         const int q = warp & 3, n2 = (wwarp >> 2) & 1;
         const int r = 32 * (q & 1) + lane;
-        uint32_t it = 0, gph = 0;
-        (void)gph;
+        uint32_t it = 0, ph0 = 0, ph1 = 0;   // phase counters: bar_acc, bar_afree[0], bar_afree[1..7]
+        (void)ph0; (void)ph1;
         for (long long rd = 0; rd < n_rounds; ++rd) {
             int tsn = 0; (void)tsn;
             const long long tile_raw = first + rd * stride;
@@ -612,38 +626,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     }
                 }
             } else if constexpr (!POST) {
-                if (!(a.dbg_skip & 4)) prep_rows<PARITY>(a, tile, wt, Ahi, Alo, taps);
-                opnd_warps_join();
+                // Tile pipeline (steady state, round rd > 0): the taps and the lin_in features of this tile, and the Y_0 staging of
+                // K blocks 1..7, were produced during the previous tile's last block; lin_in(rd) was handed off after its combine.
+                const Tap* tp = taps + (rd & 1) * ROWS;
+                Tap* tn = taps + ((rd + 1) & 1) * ROWS;
+                const bool has_next = rd + 1 < n_rounds;
+                long long tile_next = first + (rd + 1) * stride;
+                if (tile_next >= a.n_tiles) tile_next = a.n_tiles - 1;
+                if (rd == 0) {
+                    prep_rows<PARITY, NUM_OPND_WARPS * 32 / 64, true, true>(a, tile, wt, Ahi, Alo, taps);
+                    opnd_warps_join();
+                    if (!helper) worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                   // -> lin_in (K block 0 only)
+                }
                 TSW();
-                if (!helper) worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                       // -> lin_in (K block 0 only)
                 for (int b = 0; b < a.n_blocks; ++b) {
+                    const bool last = b + 1 == a.n_blocks;
                     // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gathered into the operand buffers K block by K block while the
                     // previous GEMM (lin_in / fc_1[b-1]) is still running, then added to the residual in the epilogue
-                    gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, taps, bar_afree, gph & 1); ++gph;
+                    if (b == 0 && rd > 0) {      // only K block 0 is left (it held the lin_in features until now)
+                        gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tp, 0, 0, bar_afree, ph0 & 1, ph1 & 1); ++ph0;
+                    } else {
+                        gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, tp, 0, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1);
+                        ++ph0; ++ph1;
+                    }
                     TSW();
-                    mbar_wait(bar_acc, it & 1, a.err, 40); ++it; TSW();                                                  // x complete
+                    // Helpers never wait on bar_acc in this kernel: they are gated by bar_afree alone.  (A helper that finishes a late
+                    // gather could reach a bar_acc wait after the barrier has already completed its NEXT phase -- lin_in of the next
+                    // tile is short -- and a parity wait that is one phase late blocks for good.)
+                    if (!helper) { mbar_wait(bar_acc, it & 1, a.err, 40); ++it; }                                       // x complete
+                    TSW();
                     tc_fence_after();
                     if (helper) {
-                        asm volatile("bar.arrive 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                        // staging of K blocks 6..7 complete
+                        asm volatile("bar.arrive 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                        // staging of K blocks 5..7 complete
+                        if (last && has_next) {  // taps of the next tile, while fc_0 of the last block runs
+                            if (wt - NUM_WORKERS < ROWS) prep_rows<PARITY, 1, true, false>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                            asm volatile("bar.arrive 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                        }
                     } else {
-                        asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..5 complete
+                        asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..4 complete
                         if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 0);
                         TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 0..3
                         asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
                         if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 1);
                         TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 4..7
                     }
-                    mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
-                    tc_fence_after();
                     if (!helper) {
+                        mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
+                        tc_fence_after();
                         const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
                         if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
                         TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 0..3
                         if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
                         TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 4..7
                     }
+                    if (last && has_next) {
+                        // next tile, under the last fc_1: lin_in features into K block 0 as soon as fc_1 has consumed it (helpers),
+                        // Y_0 staging of K blocks 1..7 as they are released (everyone)
+                        if (helper) {
+                            mbar_wait(bar_afree, ph0 & 1, a.err, 47);
+                            prep_rows<PARITY, NUM_HELPER_WARPS * 32 / 64, false, true>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                            fence_proxy_async();
+                            asm volatile("bar.arrive 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                    // features in place
+                        } else {
+                            asm volatile("bar.sync 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                      // next taps in place
+                        }
+                        gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1);
+                        // workers consume K block 0's phase too (the helpers did above -- and must NOT wait on it again here: by the time
+                        // they finish their late K blocks, lin_in of the next tile may already have completed the barrier's next phase)
+                        if (!helper) mbar_wait(bar_afree, ph0 & 1, a.err, 48);
+                        ++ph0; ++ph1;
+                    }
                 }
-                mbar_wait(bar_acc, it & 1, a.err, 43); ++it; TSW();
+                if (!helper) { mbar_wait(bar_acc, it & 1, a.err, 43); ++it; }                                           // fc_1 of the last block complete
+                TSW();
                 tc_fence_after();
                 // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
                 const float* cb = a.bias2 + (size_t)a.n_blocks * HID;                // b_fc1 of the last block (everything earlier is in x already)
@@ -665,6 +720,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     }
                 }
                 tc_fence_before();
+                if (has_next && !helper) {
+                    asm volatile("bar.sync 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // next tile's features in place
+                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // X read out -> lin_in of the next tile
+                }
             } else {
                 // load x_c: fp32 residual -> TMEM X, relu(x_c) -> A operand
                 long long smp = tile * ROWS + r;
@@ -890,10 +949,10 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.n_blocks = t.n_pre; post.n_blocks = t.n_post;
     pre.zmap = t.zmap; pre.zmap_stride = (long long)s.SB * s.NV * s.Hl * s.Wl * HID;
     int n = 0;
-    pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0, 1};                                // lin_in; followed by the gather of Y_0
+    pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0, 2};                                // lin_in; followed by the gather of Y_0 (K block 0)
     for (int b = 0; b < t.n_pre; ++b) {
         pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0};                 // fc_0[b]
-        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, (short)(b + 1 < t.n_pre)};   // fc_1[b]; followed by the gather of Y_{b+1}
+        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 1};                   // fc_1[b]; overlapped by the gather of Y_{b+1} / the next tile's Y_0
     }
     pre.n_steps = n;
     n = 0;
@@ -910,8 +969,9 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.err = post.err = t.err_flag;
     pre.n_total = post.n_total = total;
     pre.dbg_skip = t.dbg_skip; post.dbg_skip = 0;
-    static long long* dbg_ts = nullptr;
-    if ((t.dbg_skip & 512) && !dbg_ts) { TCK(cudaMallocManaged((void**)&dbg_ts, 8 * 64 * sizeof(long long))); memset(dbg_ts, 0, 8 * 64 * sizeof(long long)); }
+    static long long* dbg_ts = nullptr;      // device memory (managed memory would page-fault inside the kernel and distort the timeline)
+    if ((t.dbg_skip & 512) && !dbg_ts) TCK(cudaMalloc((void**)&dbg_ts, 8 * 64 * sizeof(long long)));
+    if (t.dbg_skip & 512) TCK(cudaMemsetAsync(dbg_ts, 0, 8 * 64 * sizeof(long long), st));
     pre.dbg_ts = (t.dbg_skip & 512) ? dbg_ts : nullptr; post.dbg_ts = nullptr;
     t.ms_pre = t.ms_post = 0.f;
     for (long long s0 = 0; s0 < total; s0 += sub) {
@@ -936,15 +996,17 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         }
     }
     if (pre.dbg_ts) {
+        static long long h[8 * 64];
         TCK(cudaStreamSynchronize(st));
+        TCK(cudaMemcpy(h, pre.dbg_ts, sizeof(h), cudaMemcpyDeviceToHost));
         for (int cta = 0; cta < 2; ++cta) {
-            const long long t0 = pre.dbg_ts[(cta * 4 + 1) * 64];
-            fprintf(stderr, "[ts] cta %d worker stamps (arriving, woke, arriving, ...) cycles since first:", cta);
-            for (int i = 0; i < 34; ++i) fprintf(stderr, " %lld", pre.dbg_ts[(cta * 4 + 1) * 64 + i] - t0);
+            const long long t0 = h[(cta * 4 + 1) * 64];
+            fprintf(stderr, "[ts] cta %d worker-warp-0 stamps of round %d, cycles since the first:", cta, TS_ROUND);
+            for (int i = 0; i < 40 && h[(cta * 4 + 1) * 64 + i]; ++i) fprintf(stderr, " %lld", h[(cta * 4 + 1) * 64 + i] - t0);
             fprintf(stderr, "\n");
             if (cta == 0) {
                 fprintf(stderr, "[ts] cta 0 mma stamps per step (half 0 ready, half 1 ready, committed, -), same origin:");
-                for (int i = 0; i < 28; ++i) fprintf(stderr, " %lld", pre.dbg_ts[i] ? pre.dbg_ts[i] - t0 : 0);
+                for (int i = 0; i < 28; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - t0 : 0);
                 fprintf(stderr, "\n");
             }
         }

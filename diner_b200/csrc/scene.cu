@@ -22,7 +22,42 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
         if (p < HW && c < C) d[(size_t)p * C + c] = tile[threadIdx.x][i];
     }
 }
+
+// Target-view rays [o3, d3, near, far] for every pixel centre (src/util/cam_geometry.py:5-48), one thread per pixel.
+// Op order follows the reference's torch sequence: (screen - c) / focal, / sqrt((px^2 + py^2) + 1), then the K=3 matmul form
+// fma(r2,z, fma(r1,y, r0*x)) with R^T (see common.cuh dot3_rm); origin = (-R^T) t.
+__global__ void gen_rays_kernel(const float* __restrict__ ext, const float* __restrict__ intr, int SB, int H, int W, float z_near,
+                                float z_far, float* __restrict__ rays) {
+    const long long n = (long long)SB * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int sb = (int)(i / ((long long)H * W));
+        const int pix = (int)(i % ((long long)H * W));
+        const int y = pix / W, x = pix % W;
+        const float* E = ext + (size_t)sb * 16;
+        const float* Kp = intr + (size_t)sb * 9;
+        const float px = __fdiv_rn(__fsub_rn((float)x + 0.5f, __ldg(Kp + 2)), __ldg(Kp + 0));
+        const float py = __fdiv_rn(__fsub_rn((float)y + 0.5f, __ldg(Kp + 5)), __ldg(Kp + 4));
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), 1.0f));
+        const float dx = __fdiv_rn(px, nrm), dy = __fdiv_rn(py, nrm), dz = __fdiv_rn(1.0f, nrm);
+        float o[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float r0 = __ldg(E + k), r1 = __ldg(E + 4 + k), r2 = __ldg(E + 8 + k);      // row k of R^T = column k of R
+            d[k] = fmaf(r2, dz, fmaf(r1, dy, __fmul_rn(r0, dx)));
+            o[k] = fmaf(-r2, __ldg(E + 11), fmaf(-r1, __ldg(E + 7), __fmul_rn(-r0, __ldg(E + 3))));
+        }
+        float4* dst = (float4*)(rays + i * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], d[0]);
+        dst[1] = make_float4(d[1], d[2], z_near, z_far);
+    }
+}
 }  // namespace
+
+cudaError_t launch_gen_rays(const float* ext, const float* intr, int SB, int H, int W, float z_near, float z_far, float* rays,
+                            int num_sms, cudaStream_t st) {
+    gen_rays_kernel<<<num_sms * 8, 256, 0, st>>>(ext, intr, SB, H, W, z_near, z_far, rays);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, cudaStream_t st) {
     dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);

@@ -64,6 +64,16 @@ class NeRFRendererDGS(torch.nn.Module):
             self.white_bkgd, model.mode_id(), self._noise_for_call(), want_weights=want_weights)
         return DotMap(fine=self._format_outputs(w, rgb, depth, want_weights))
 
+    @torch.no_grad()
+    def render_image(self, model, target_extrinsics, target_intrinsics, H, W, z_near, z_far):
+        """Whole target view(s) in ONE library call: gen_rays (src/util/cam_geometry.py:5-48) + the ray_batch_size split /
+        torch.cat loop of DINER.predict_imgs_from_batch (src/models/diner.py:79-92).  -> rgb (SB,H*W,3), depth (SB,H*W)."""
+        noise = self._noise_for_call()
+        return model.context().render_image(
+            target_extrinsics.float().contiguous(), target_intrinsics.float().contiguous(), int(H), int(W), float(z_near),
+            float(z_far), int(self.n_samples), int(self.n_depth_candidates), int(self.n_gaussian), self.white_bkgd,
+            model.mode_id(), dict(seed=noise.get("seed", 0)))
+
     def _format_outputs(self, weights, rgb, depth, want_weights):
         out = DotMap(rgb=rgb, depth=depth)
         if want_weights:

@@ -89,6 +89,17 @@ int diner_render(diner_ctx* ctx, const float* rays, int SB, int NR, int K, int C
                  int mode, const diner_noise* noise, float* rgb, float* depth, float* weights, float* z,
                  void* stream);
 
+/* Whole-image entry: ray generation (gen_rays, src/util/cam_geometry.py:5-48) + the ray_batch_size chunk loop and torch.cat of
+ * DINER.predict_imgs_from_batch (src/models/diner.py:79-92) in one call.  target_extrinsics (SB,4,4) world->cam, target_intrinsics
+ * (SB,3,3), device fp32; rays are generated on the device for every pixel centre of the H x W target view (row-major) and never
+ * leave the library; rgb (SB,H*W,3), depth (SB,H*W). */
+int diner_render_image(diner_ctx* ctx, const float* target_extrinsics, const float* target_intrinsics, int SB, int H, int W,
+                       float z_near, float z_far, int K, int C, int G, int white_bkgd, int mode, const diner_noise* noise,
+                       float* rgb, float* depth, void* stream);
+/* gen_rays alone (src/util/cam_geometry.py:5-48): rays (SB,H*W,8) = [origin3, dir3, near, far]. */
+int diner_gen_rays(diner_ctx* ctx, const float* target_extrinsics, const float* target_intrinsics, int SB, int H, int W,
+                   float z_near, float z_far, float* rays, void* stream);
+
 /* Same call with HOST buffers (rays in, rgb/depth out): copies host->device, renders, copies back and
  * synchronises the stream.  This is the end-to-end entry a non-torch caller uses. */
 int diner_render_host(diner_ctx* ctx, const float* rays_host, int SB, int NR, int K, int C, int G,

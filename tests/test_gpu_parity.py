@@ -210,3 +210,42 @@ def test_full_size_properties():
         fg = float((full.fine.depth > 0).float().mean())
         print("full-size: %.1f %% of rays hit geometry, rgb mean %.3f" % (100 * fg, float(full.fine.rgb.mean())))
         assert fg > 0.05
+
+
+def test_whole_image_entry_matches_ray_batches():
+    """diner_render_image (in-library gen_rays + whole-image launch) against the reference flow:
+    gen_rays (cam_geometry.py:5-48, restated in diner_b200.synthetic) + renderer.forward per ray batch of 4096 + cat."""
+    from diner_b200 import synthetic as S
+    from diner_b200.predict import predict_imgs_from_batch
+    cfg = dict(H=64, W=96, NV=4, SB=2, near=1.0, far=2.5, K=32, C=200, G=12, white=True, nr=16, seed=3)
+    batch, latent, mlp, _, _ = MG.case_inputs(cfg)
+    model = product_model(batch, latent, mlp, "cuda", "parity")
+    rend = renderer_for(cfg)
+    rend.noise = dict(seed=77)
+    ext, intr = batch["target_extrinsics"].cuda(), batch["target_intrinsics"].cuda()
+    SB, H, W = cfg["SB"], cfg["H"], cfg["W"]
+    rays_ref = S.gen_rays(batch["target_extrinsics"], batch["target_intrinsics"], W, H, torch.full((SB,), cfg["near"]),
+                          torch.full((SB,), cfg["far"])).view(SB, H * W, 8)
+    rays_dev = model.context().gen_rays(ext, intr, H, W, cfg["near"], cfg["far"])
+    err = (rays_dev.cpu() - rays_ref).abs().max()
+    exact = (rays_dev.cpu() == rays_ref).float().mean()
+    print("gen_rays: max |err| %.3g, bit-exact fraction %.4f" % (err, exact))
+    assert err <= 2.5e-7 and exact >= 0.5       # 1-ulp differences in the K=3 products of a minority of the rays
+    with torch.no_grad():
+        whole = rend(model, rays_dev)                                   # one call over all rays, same seed
+        b = dict(batch, target_rgb=torch.empty(SB, 3, H, W))
+        b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+        rgb, depth = predict_imgs_from_batch(model, rend, b, cfg["near"], cfg["far"], return_depth=True, encode=False)
+    assert rgb.shape == (SB, 3, H, W) and depth.shape == (SB, 1, H, W)
+    assert torch.equal(rgb.permute(0, 2, 3, 1).reshape(SB, H * W, 3), whole.fine.rgb)
+    assert torch.equal(depth.reshape(SB, H * W), whole.fine.depth)
+    # and against the CPU oracle on the reference's rays (stage-wise: same sample depths)
+    ctx = model.context()
+    z = ctx.sample(rays_dev, cfg["K"], cfg["C"], cfg["G"], dict(seed=77))
+    scene = O.make_scene_state(batch, latent, mlp)
+    sub = slice(0, 512)
+    _, rgb_o, depth_o = O.composite(scene, rays_ref[:, sub], z[:, sub].cpu(), cfg["white"])
+    _, rgb_p, depth_p = ctx.composite(rays_dev[:, sub].contiguous(), z[:, sub].contiguous(), cfg["white"], 1)
+    e = max(float((rgb_p.cpu() - rgb_o).abs().max()), float((depth_p.cpu() - depth_o).abs().max()))
+    print("whole-image entry: composite vs oracle on 512 rays/scene: max |err| %.3g" % e)
+    assert e <= TOL
