@@ -286,7 +286,10 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "tc2::mlp_pair_kernel<PRE> (per sample-view ResnetFC layers; algorithmic FLOPs incl. the hoisted lin_z)",
                          "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["sustained"], "peak_source": pk["src"] + " bf16 dense sustained",
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one PRE launch (524 288 samples) from the ncu --set full
+                         # capture summarised in profiles/r1d_ncu_mlp_pair.md (parity mode); not re-measured by this run
+                         "traffic": 2.998e9 if args.mode == "parity" else None,
+                         "traffic_source": "ncu --set full, profiles/r1d_ncu_mlp_pair.md (bytes per PRE launch)",
                          "whole_step_frac": rays_per_s / world * K * FLOP_PER_SAMPLE / 1e12 / pk["sustained"],
                          "executed_flop_multiplier": 3 if args.mode == "parity" else 1,
                          "stage_ms_per_step": stage,
