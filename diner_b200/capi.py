@@ -36,6 +36,7 @@ SIGNATURES = {
     "diner_render": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P, _P, _P]),
     "diner_render_image": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
     "diner_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P]),
+    "diner_depth2normal": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "diner_render_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _U64, _P, _P, _P]),
     "diner_sample": (_I, [_P, _P, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
     "diner_query": (_I, [_P, _P, _P, _I, _LL, _I, _P, _P]),
@@ -101,7 +102,7 @@ class Context:
         self.handle = h
         self._keep = []
         for key, env in (("cluster", "DINER_TC_CLUSTER"), ("sub_batch", "DINER_TC_SUB_BATCH"), ("kernel", "DINER_TC_KERNEL"),
-                         ("dbg_skip", "DINER_TC_DBG_SKIP")):
+                         ("dbg_skip", "DINER_TC_DBG_SKIP"), ("early_split", "DINER_TC_EARLY_SPLIT")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))
 
@@ -209,6 +210,16 @@ class Context:
                 _ptr(target_intrinsics, (SB, 3, 3), "target_intrinsics"), SB, H, W, float(z_near), float(z_far),
                 _ptr(rays), _stream(self.device)))
         return rays
+
+    def depth2normal(self, depths, intrinsics):
+        """src/util/depth2normal.py:6-87 on the device: depths (N,1,H,W), intrinsics (N,3,3) -> (N,3,H,W)."""
+        N, _, H, W = depths.shape
+        normals = torch.empty(N, 3, H, W, device=depths.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.diner_depth2normal(self.handle, _ptr(depths, (N, 1, H, W), "depths"),
+                                                    _ptr(intrinsics, (N, 3, 3), "intrinsics"), N, H, W, _ptr(normals),
+                                                    _stream(self.device)))
+        return normals
 
     def sample(self, rays, K, C, G, noise=None, want_dgs=False):
         SB, NR, _ = rays.shape

@@ -360,6 +360,17 @@ extern "C" int diner_render(diner_ctx* c, const float* rays, int SB, int NR, int
     return rc;
 }
 
+extern "C" int diner_depth2normal(diner_ctx* c, const float* depths, const float* intrinsics, int N, int H, int W, float* normals,
+                                  void* stream) {
+    if (!c) return fail(DINER_E_INVALID, "ctx is NULL");
+    if (N < 1 || H < 1 || W < 1) return fail(DINER_E_INVALID, "bad N=%d H=%d W=%d", N, H, W);
+    if (!depths || !intrinsics || !normals) return fail(DINER_E_INVALID, "NULL pointer argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(launch_depth2normal(depths, intrinsics, N, H, W, normals, c->num_sms, (cudaStream_t)stream));
+    g_launches++; c->launches++;
+    return DINER_OK;
+}
+
 extern "C" int diner_gen_rays(diner_ctx* c, const float* target_extrinsics, const float* target_intrinsics, int SB, int H, int W,
                               float z_near, float z_far, float* rays, void* stream) {
     if (!c) return fail(DINER_E_INVALID, "ctx is NULL");
@@ -416,6 +427,9 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     } else if (!strcmp(key, "kernel")) {
         if (value != 1 && value != 2) return fail(DINER_E_INVALID, "kernel must be 1 (single-CTA) or 2 (CTA pair)");
         c->tc.kernel = (int)value;
+    } else if (!strcmp(key, "early_split")) {
+        if (value < 1 || value > 7) return fail(DINER_E_INVALID, "early_split must be in [1,7]");
+        c->tc.early_split = (int)value;
     } else if (!strcmp(key, "rebuild_maps")) {
         c->tc.zmap_valid = false;        // next query rebuilds the hoisted lin_z maps (bench: times the scene-prepare step)
     } else if (!strcmp(key, "dbg_skip")) {

@@ -60,5 +60,6 @@ cudaError_t launch_composite(const float* rays, const float* z, const float* net
 cudaError_t launch_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, cudaStream_t st);
 cudaError_t launch_gen_rays(const float* ext, const float* intr, int SB, int H, int W, float z_near, float z_far, float* rays,
                             int num_sms, cudaStream_t st);
+cudaError_t launch_depth2normal(const float* depth, const float* intr, int N, int H, int W, float* normals, int num_sms, cudaStream_t st);
 cudaError_t upload_std_ring_gain();
 extern long long g_launches;   // bumped at every kernel launch site

@@ -800,6 +800,11 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             t.wmap_ok = (r == CUDA_SUCCESS);
+            cuuint32_t box16[2] = {64, 16};
+            r = ((EncodeFn)fn)(&t.wmap_small, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t.wpack, gdim, gstr, box16, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            t.wmap_small_ok = t.wmap_ok && (r == CUDA_SUCCESS);
         }
         (void)cudaGetLastError();
     }

@@ -29,6 +29,9 @@ struct TcState {
     float ms_zmap = 0.f;          // device time of the last Y-map build (timing enabled)
     CUtensorMap wmap;             // 2-D view of wpack: rows of 128 B, box = one 16 KiB tile (pair kernel: cta_group::2 TMA)
     bool wmap_ok = false;
+    CUtensorMap wmap_small;       // same buffer, box = first 16 rows of a tile (2 KiB): lin_out in the pair kernel
+    bool wmap_small_ok = false;
+    int early_split = 5;          // pair kernel PRE: worker/helper split of the next tile's early Y_0 gather (tuning)
     int dbg_skip = 0;             // profiling experiments (pair kernel PRE): see tc2::Args::dbg_skip
     bool timing = false;          // per-kernel CUDA-event timing (adds one sync per sub-batch)
     float ms_pre = 0.f, ms_post = 0.f;   // accumulated over the last tc_query call

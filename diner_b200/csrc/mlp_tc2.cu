@@ -52,6 +52,8 @@ constexpr int ROWS = 64;                    // rows per CTA (128 per pair)
 constexpr int HID = 512;
 constexpr int KBLK = 64;
 constexpr int WTILE_BYTES = 128 * KBLK * 2; // 16 KiB: 128 hidden rows x 64 k, K-major SWIZZLE_128B (same packing as mlp_tc.cu)
+constexpr int SMALL_TILE_BYTES = 16 * KBLK * 2; // 2 KiB: the first 16 rows of a weight tile (lin_out)
+constexpr int TILE_SMALL = 1 << 30;             // tile-table flag: load only SMALL_TILE_BYTES of this tile
 constexpr int ACT_KB_BYTES = ROWS * 128;    // 8 KiB per 64-wide K block of the activation operand
 constexpr int ACT_BYTES = ACT_KB_BYTES * (HID / KBLK);   // 64 KiB per bf16 copy
 constexpr int NUM_THREADS = 512;
@@ -84,6 +86,7 @@ struct GemmStep {
 
 struct Args {
     CUtensorMap wmap;           // packed weight stream as rows of 128 B; one box = one 16 KiB tile
+    CUtensorMap wmap_small;     // same stream, box = the first 16 rows (2 KiB) of a tile: lin_out (N = 32 over the pair) needs no more
     SceneDev s;
     QueryArgs q;
     const uint8_t* wstream;     // packed weight tiles (16 KiB units), shared with mlp_tc.cu's packing
@@ -101,6 +104,7 @@ struct Args {
     long long n_pix;            // ZMAP: latent pixels (SB*NV*Hl*Wl)
     int* err;
     long long* dbg_ts;          // profiling: clock64 stamps of pair 0 in round 1 ([cta][role][slot])
+    int early_worker_kb_hi;     // next-tile Y_0 gather under the last fc_1: K blocks 1..this on the workers, the rest on the helpers
     int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
 };
 
@@ -252,10 +256,9 @@ __device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, ui
 // which are released when that GEMM is about to finish -- the workers run the first epilogue half meanwhile.
 __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ ymap, int wwarp, int lane, uint8_t* Ahi,
                                          uint8_t* Alo, const Tap* taps, int kb_lo, int kb_hi, uint32_t bar_afree, uint32_t par0,
-                                         uint32_t par1) {
+                                         uint32_t par1, int WORKER_KB_HI = 4) {
     const SceneDev& s = a.s;
     constexpr int PASSES_PER_KB = ROWS / 4;         // 16
-    constexpr int WORKER_KB_HI = 4;
     auto issue = [&](int p, float4 (&f)[8], float (&w)[4], uint32_t& off) {
         const int kb = p / PASSES_PER_KB, r = 4 * (p % PASSES_PER_KB) + (lane >> 3);
         const Tap rt = taps[r];
@@ -294,9 +297,11 @@ __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ y
         const int p2 = p + p_step;
         const bool two = p2 < p_end;
         const int kb_need = (two ? p2 : p) / PASSES_PER_KB;
-        while (waited < kb_need) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 45); }
+        // the global loads do not touch the operand buffers: issue them BEFORE waiting for the K block's release, so that
+        // their latency overlaps the wait and only the staging stores are gated by the barrier
         issue(p, fa, wa, oa);
         if (two) issue(p2, fb, wb, ob);
+        while (waited < kb_need) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 45); }
         finish(fa, wa, oa);
         if (two) finish(fb, wb, ob);
     }
@@ -515,10 +520,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 const uint32_t ph = (uint32_t)((use / C::NST) & 1);
                 mbar_wait(bar_empty + 8 * st, ph ^ 1, a.err, 10);
                 if (leader) {
-                    if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, 2 * WTILE_BYTES);
-                    const int row = __ldg(table + t) * 128;
+                    const int tix = __ldg(table + t);
+                    const bool small = (tix & TILE_SMALL) != 0;          // lin_out: only the first 16 rows of the tile are read
+                    const int row = (tix & (TILE_SMALL - 1)) * 128;
+                    if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, small ? 2 * SMALL_TILE_BYTES : 2 * WTILE_BYTES);
                     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(smem_base + st * WTILE_BYTES), "l"(&a.wmap), "r"(0), "r"(row), "r"(leader_full + 8 * st) : "memory");
+                                 ::"r"(smem_base + st * WTILE_BYTES), "l"(small ? &a.wmap_small : &a.wmap), "r"(0), "r"(row), "r"(leader_full + 8 * st) : "memory");
                 }
                 __syncwarp();
             }
@@ -660,6 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         asm volatile("bar.arrive 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                        // staging of K blocks 5..7 complete
                         if (last && has_next) {  // taps of the next tile, while fc_0 of the last block runs
                             if (wt - NUM_WORKERS < ROWS) prep_rows<PARITY, 1, true, false>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                            asm volatile("bar.sync 9, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");                    // all helpers read these taps below
                             asm volatile("bar.arrive 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
                         }
                     } else {
@@ -690,7 +698,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         } else {
                             asm volatile("bar.sync 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                      // next taps in place
                         }
-                        gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1);
+                        gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.early_worker_kb_hi);
                         // workers consume K block 0's phase too (the helpers did above -- and must NOT wait on it again here: by the time
                         // they finish their late K blocks, lin_in of the next tile may already have completed the barrier's next phase)
                         if (!helper) mbar_wait(bar_afree, ph0 & 1, a.err, 48);
@@ -829,14 +837,14 @@ static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cu
     const int kbz = m.d_latent / KBLK, kbh = HID / KBLK;
     std::vector<int> zm[2], pre[2], post[2];
     int layer_pair0 = 0;
-    auto layer = [&](std::vector<int>* tab, bool par, int nkb, int n_mt, int n_tiles) {
+    auto layer = [&](std::vector<int>* tab, bool par, int nkb, int n_mt, int n_tiles, int flag = 0) {
         if (tab)
             for (int r = 0; r < 2; ++r)
                 for (int kb = 0; kb < nkb; ++kb)
                     for (int n2 = 0; n2 < n_tiles; ++n2) {
                         const int pair = layer_pair0 + (2 * n2 + r) * nkb + kb;
-                        tab[r].push_back(2 * pair);
-                        if (par) tab[r].push_back(2 * pair + 1);
+                        tab[r].push_back((2 * pair) | flag);
+                        if (par) tab[r].push_back((2 * pair + 1) | flag);
                     }
         layer_pair0 += n_mt * nkb;
     };
@@ -847,7 +855,7 @@ static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cu
         layer(pre, parity, kbh, 4, 2);                               // fc_1[b]
     }
     for (int b = 0; b < t.n_post; ++b) { layer(post, parity, kbh, 4, 2); layer(post, parity, kbh, 4, 2); }
-    layer(post, parity, kbh, 2, 1);                                  // lin_out packed as 2 M-tiles (second is zeros)
+    layer(post, parity, kbh, 2, 1, t.wmap_small_ok ? TILE_SMALL : 0);   // lin_out packed as 2 M-tiles (second is zeros); 16 rows of each suffice
     t.uses2_zmap = (int)zm[0].size(); t.uses2_pre = (int)pre[0].size(); t.uses2_post = (int)post[0].size();
     std::vector<int> flat;
     for (int r = 0; r < 2; ++r) flat.insert(flat.end(), zm[r].begin(), zm[r].end());
@@ -888,7 +896,7 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
         t.zmap_bytes = need;
     }
     Args z{};
-    z.wmap = t.wmap;
+    z.wmap = t.wmap; z.wmap_small = t.wmap_small;
     z.s = s;
     z.wstream = (const uint8_t*)t.wpack;
     z.tile_table = t.table2;
@@ -940,6 +948,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     }
     Args pre{}, post{};
     pre.wmap = post.wmap = t.wmap;
+    pre.wmap_small = post.wmap_small = t.wmap_small;
     pre.s = s; pre.q = q; post.s = s; post.q = q;
     pre.wstream = post.wstream = (const uint8_t*)t.wpack;
     pre.tile_table = t.table2 + 2 * t.uses2_zmap; post.tile_table = pre.tile_table + 2 * t.uses2_pre;
@@ -969,6 +978,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.err = post.err = t.err_flag;
     pre.n_total = post.n_total = total;
     pre.dbg_skip = t.dbg_skip; post.dbg_skip = 0;
+    pre.early_worker_kb_hi = t.early_split;
     static long long* dbg_ts = nullptr;      // device memory (managed memory would page-fault inside the kernel and distort the timeline)
     if ((t.dbg_skip & 512) && !dbg_ts) TCK(cudaMalloc((void**)&dbg_ts, 8 * 64 * sizeof(long long)));
     if (t.dbg_skip & 512) TCK(cudaMemsetAsync(dbg_ts, 0, 8 * 64 * sizeof(long long), st));

@@ -50,7 +50,11 @@ class PixelNeRF(torch.nn.Module):
     def encode(self, images, depths, depths_std, extrinsics, intrinsics):
         """Feature maps + camera buffers for the following forward() calls (pixelnerf.py:35-53)."""
         images = self.normalize_rgb(images)
-        normals = depth2normal(depths.flatten(end_dim=1), intrinsics.flatten(end_dim=1)).reshape_as(images)
+        if depths.is_cuda:      # CUDA kernel (diner_depth2normal); the torch version only serves CPU-side module tests
+            normals = self._bare_context(depths.device).depth2normal(
+                depths.flatten(end_dim=1).float().contiguous(), intrinsics.flatten(end_dim=1).float().contiguous()).reshape_as(images)
+        else:
+            normals = depth2normal(depths.flatten(end_dim=1), intrinsics.flatten(end_dim=1)).reshape_as(images)
         self.encoder(images, depths, depths_std, normals)
         self.set_cameras(extrinsics, intrinsics, images.shape[-1], images.shape[-2])
 
@@ -63,14 +67,19 @@ class PixelNeRF(torch.nn.Module):
         self._scene_stamp = None
 
     # ------------------------------------------------------------------------------------------
-    def context(self):
-        """libdiner_b200 context with the current parameters and scene uploaded (lazy, versioned)."""
-        dev = self.poses.device
+    def _bare_context(self, dev):
         if dev.type != "cuda":
             raise RuntimeError("diner_b200 renders on CUDA only; move the model and batch to a B200 (got %s)" % dev)
+        dev = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         if self._ctx is None or self._ctx.device != dev:
             self._ctx = capi.Context(dev)
             self._mlp_stamp = self._scene_stamp = None
+        return self._ctx
+
+    def context(self):
+        """libdiner_b200 context with the current parameters and scene uploaded (lazy, versioned)."""
+        dev = self.poses.device
+        self._bare_context(dev)
         m = self.mlp_fine
         if getattr(m, "beta", 0.0) > 0:
             raise NotImplementedError("softplus ResnetFC (beta > 0) is not supported by libdiner_b200")

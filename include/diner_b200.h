@@ -100,6 +100,11 @@ int diner_render_image(diner_ctx* ctx, const float* target_extrinsics, const flo
 int diner_gen_rays(diner_ctx* ctx, const float* target_extrinsics, const float* target_intrinsics, int SB, int H, int W,
                    float z_near, float z_far, float* rays, void* stream);
 
+/* Scene prepare: depth2normal (src/util/depth2normal.py:6-87, called by PixelNeRF.encode, pixelnerf.py:41-42):
+ * depths (N,1,H,W), intrinsics (N,3,3) -> normals (N,3,H,W), zero where there is no depth. */
+int diner_depth2normal(diner_ctx* ctx, const float* depths, const float* intrinsics, int N, int H, int W, float* normals,
+                       void* stream);
+
 /* Same call with HOST buffers (rays in, rgb/depth out): copies host->device, renders, copies back and
  * synchronises the stream.  This is the end-to-end entry a non-torch caller uses. */
 int diner_render_host(diner_ctx* ctx, const float* rays_host, int SB, int NR, int K, int C, int G,

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     from diner_b200 import capi
     lib = capi.load_library()
     header = open(os.path.join(ROOT, "include", "diner_b200.h")).read()
-    declared = set(re.findall(r"\b(diner_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(diner_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     for name in declared:
         assert hasattr(lib, name), "libdiner_b200.so does not export %s" % name

@@ -249,3 +249,56 @@ def test_whole_image_entry_matches_ray_batches():
     e = max(float((rgb_p.cpu() - rgb_o).abs().max()), float((depth_p.cpu() - depth_o).abs().max()))
     print("whole-image entry: composite vs oracle on 512 rays/scene: max |err| %.3g" % e)
     assert e <= TOL
+
+
+@pytest.mark.parametrize("H,W,seed", [(64, 64, 1), (48, 64, 3), (96, 128, 5)])
+def test_depth2normal_kernel_matches_oracle(H, W, seed):
+    """diner_depth2normal (scene prepare) against the CPU oracle's restatement of
+    src/util/depth2normal.py:6-87 -- bit-exact (the op order was pinned by emulation), NaN pattern included."""
+    from diner_b200 import synthetic as S
+    from diner_b200.capi import Context
+    batch = S.make_scene(H, W, 4, 2, 1.0, 2.5, seed)
+    dm = batch["src_depths"].flatten(end_dim=1)
+    K = batch["src_intrinsics"].flatten(end_dim=1)
+    ref = O.depth2normal(dm, K)
+    out = Context("cuda").depth2normal(dm.cuda().contiguous(), K.cuda().contiguous()).cpu()
+    same = (out == ref) | (torch.isnan(out) & torch.isnan(ref))
+    print("depth2normal %dx%d: bit-exact fraction %.5f, max |err| %.3g" % (
+        H, W, same.float().mean(), torch.nan_to_num(out - ref).abs().max()))
+    assert bool(same.all())
+
+
+@pytest.mark.parametrize("name,cfg", [
+    # BASELINE.json configs[2] shape (Facescape: 256x256, 4 views, K=128, SB=4, white background), forward only
+    ("cfg3_face256", dict(H=256, W=256, NV=4, SB=4, near=1.0, far=2.5, K=128, C=1000, G=48, white=True, nr=384, seed=11)),
+    # configs[4] shape (stress: 8 views, K=256) on a 256x256 scene
+    ("cfg5_nv8_k256", dict(H=256, W=256, NV=8, SB=1, near=0.3211, far=1.2041, K=256, C=1000, G=96, white=False, nr=256, seed=12)),
+])
+def test_other_config_shapes_forward(name, cfg):
+    """The other BASELINE.json configs as parity-test cases: tcgen05 parity mode against the fp32 CUDA-core
+    mode (reference arithmetic, itself pinned to the goldens) at those shapes, plus the CPU oracle on a few rays."""
+    from diner_b200 import synthetic as S
+    H, W, SB, NV = cfg["H"], cfg["W"], cfg["SB"], cfg["NV"]
+    batch = S.make_scene(H, W, NV, SB, cfg["near"], cfg["far"], cfg["seed"])
+    gen = torch.Generator().manual_seed(cfg["seed"])         # (the hash-based fixture latent is too slow to build at this size)
+    latent = torch.randn(SB, NV, 512, (H + 128) // 2, (W + 128) // 2, generator=gen) * 0.5
+    mlp = S.make_mlp_state(seed=cfg["seed"])
+    rays = S.gen_rays(batch["target_extrinsics"], batch["target_intrinsics"], W, H, torch.full((SB,), cfg["near"]),
+                      torch.full((SB,), cfg["far"])).view(SB, H * W, 8)
+    rays = rays[:, (torch.arange(cfg["nr"]) * (H * W // cfg["nr"]) + 7) % (H * W)].contiguous()
+    model = product_model(batch, latent, mlp, "cuda", "parity")
+    ctx = model.context()
+    r = rays.cuda()
+    nz = dict(seed=5)
+    z = ctx.sample(r, cfg["K"], cfg["C"], cfg["G"], nz)
+    assert bool((z[..., 1:] >= z[..., :-1]).all())
+    w_p, rgb_p, d_p = ctx.composite(r, z, cfg["white"], 1)
+    w_f, rgb_f, d_f = ctx.composite(r, z, cfg["white"], 0)
+    e = max(float((rgb_p - rgb_f).abs().max()), float((d_p - d_f).abs().max()))
+    scene = O.make_scene_state(batch, latent, mlp)
+    sub = slice(0, 24)
+    _, rgb_o, d_o = O.composite(scene, rays[:, sub], z[:, sub].cpu(), cfg["white"])
+    eo = max(float((rgb_p[:, sub].cpu() - rgb_o).abs().max()), float((d_p[:, sub].cpu() - d_o).abs().max()))
+    print("%s: parity vs fp32 max |err| %.3g; parity vs CPU oracle (24 rays/scene) %.3g" % (name, e, eo))
+    assert e <= TOL and eo <= TOL
+    assert float(w_p.min()) >= 0.0 and float(w_p.sum(-1).max()) <= 1.0 + 1e-5
