@@ -791,6 +791,7 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
         t.wmap_ok = false;
+        t.wmap_small_ok = false;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
             cuuint64_t gdim[2] = {64, (cuuint64_t)(t.pairs_pre + t.pairs_post) * 2 * 128};
             cuuint64_t gstr[1] = {128};
