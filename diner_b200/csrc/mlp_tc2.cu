@@ -816,12 +816,9 @@ template <bool PARITY, int KIND>
 cudaError_t launch(const Args& a, int grid, cudaStream_t st) {
     auto kern = mlp_pair_kernel<PARITY, KIND>;
     constexpr int smem = Cfg<PARITY>::SMEM_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // per launch (a few hundred ns): the attribute is per device, and one process may drive several
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
     g_launches++;
     kern<<<grid, NUM_THREADS, smem, st>>>(a);
     return cudaGetLastError();

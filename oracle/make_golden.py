@@ -132,10 +132,36 @@ def run_reference(ns, cfg, batch, latent, mlp, rays, noise):
                 normals=model.encoder.normals.clone())
 
 
+GEN_RAYS_CASES = {   # name: H, W, SB, near, far, seed  (caller side of the hot path: src/util/cam_geometry.py:5-48)
+    "gen_rays_24x16": dict(H=16, W=24, SB=2, near=1.0, far=2.5, seed=3),
+    "gen_rays_64x96": dict(H=64, W=96, SB=2, near=0.3211, far=1.2041, seed=3),
+}
+
+
+def gen_rays_inputs(cfg):
+    batch = S.make_scene(cfg["H"], cfg["W"], 4, cfg["SB"], cfg["near"], cfg["far"], cfg["seed"])
+    return batch["target_extrinsics"], batch["target_intrinsics"]
+
+
+def make_gen_rays_golden(ns, outdir):
+    """Rays of the UNMODIFIED reference gen_rays for the synthetic target cameras (pins diner_b200.synthetic.gen_rays,
+    the restatement the tests feed to every render, and through it diner_gen_rays / diner_render_image)."""
+    out = {}
+    for name, cfg in GEN_RAYS_CASES.items():
+        E, K = gen_rays_inputs(cfg)
+        rays = ns.cam_geometry.gen_rays(E, K, cfg["W"], cfg["H"], torch.full((cfg["SB"],), cfg["near"]),
+                                        torch.full((cfg["SB"],), cfg["far"]))
+        out[name] = dict(cfg=cfg, rays=rays.contiguous())
+    torch.save(out, os.path.join(outdir, "gen_rays.pt"))
+
+
 def main():
     ns = ref_import.load()
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    make_gen_rays_golden(ns, outdir)
+    if "--rays-only" in sys.argv:
+        return
     for name, cfg in CASES.items():
         batch, latent, mlp, rays, noise = case_inputs(cfg)
         ref = run_reference(ns, cfg, batch, latent, mlp, rays, noise)
