@@ -92,12 +92,17 @@ def build_inputs():
     return batch, latent, mlp, rays
 
 
+def strided_pick(n_rays):
+    """Indices of a bounded, strided sample of the image's rays (every value < H*W for any n_rays <= H*W)."""
+    return (torch.arange(n_rays) * (H * W // n_rays) + 131) % (H * W)
+
+
 def cpu_baseline(batch, latent, mlp, rays, n_rays=12288, warm=256):
     """The oracle port (torch-CPU restatement pinned to the reference) on this box's host cores, bounded sample."""
     from oracle import diner_oracle as O
     from diner_b200 import synthetic as S
     scene = O.make_scene_state(batch, latent, mlp)
-    pick = torch.arange(n_rays) * (H * W // n_rays) + 131
+    pick = strided_pick(n_rays)
     r = rays[:, pick].contiguous()
 
     def run(rr):

@@ -53,3 +53,12 @@ def test_shard_bounds_cover_everything():
             spans = [shard_bounds(n, world, r)[:2] for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_bench_sample_indices_in_range():
+    """bench.py's bounded CPU samples (cpu_baseline / --impl reference) must index inside the 512x512 ray list."""
+    import bench
+    for n in (64, 1024, 4096, 12288, bench.H * bench.W):
+        p = bench.strided_pick(n)
+        assert p.numel() == n and int(p.min()) >= 0 and int(p.max()) < bench.H * bench.W
+        assert p.unique().numel() == n
