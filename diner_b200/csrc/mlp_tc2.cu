@@ -19,7 +19,17 @@
 //   lin_z[b](bilinear(latent, uv)) == bilinear(lin_z[b](latent), uv)      (the four tap weights sum to 1)
 // and Y_b = W_z[b] . latent is computed ONCE per (scene, weights) for every latent pixel by the ZMAP variant of this kernel
 // (bf16x3, fp32 maps [b][pixel][512]).  The PRE kernel then gathers Y_b bilinearly and adds it to the fp32 residual in TMEM:
-// one third of the per-sample-view GEMM work and weight streaming disappears.  Biases stay in the cumulative vectors.
+// one third of the per-sample-view GEMM work and weight streaming disappears.  The biases that enter a block (b_in / b_fc1[b-1],
+// b_z[b]) are folded into Y_b; b_fc0 is added by the net epilogue, b_fc1 of the last block when the combined x_c is written.
+//
+// Software pipeline (everything in place: parity mode has neither spare shared memory nor spare TMEM):
+//   * GEMM steps run K-block-outer; the issuer commits bar_afree[kb] after the last MMA that reads operand K block kb;
+//   * the gathered Y_b rows are staged as fp32 INSIDE the operand buffers (hi slot + lo slot of each 8-channel chunk),
+//     K block by K block behind bar_afree while fc_1 of the previous block still runs (loads are issued before the wait);
+//   * epilogues run in two halves (K blocks 0..3 / 4..7), one operand barrier each, so the next GEMM starts on half 0;
+//   * across tiles: under the last fc_1 the helper warps compute the next tile's taps and lin_in features and everyone gathers
+//     its Y_0 (K blocks 1..7); lin_in of the next tile is handed off right after the view-combine.
+// mbarrier parity waits are only safe if the waiter cannot be a whole phase late -- see the notes at the helper-warp code.
 //
 // Reference semantics: src/models/resnetfc.py:61-69,129-159; src/models/pixelnerf.py:91-143; src/models/image_encoder.py:97-146.
 #include "mlp_tc.h"
