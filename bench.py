@@ -32,6 +32,25 @@ SEED = 0
 FLOP_PER_SAMPLE = 4774912 * NV + 2101248       # algorithmic MLP FLOPs per sample
 FLOP_PRE_PER_SAMPLE = 4774912 * NV             # ... of which in the per-sample-view (PRE) kernel
 WORKLOAD = "DTU-shaped synthetic 512x512, 4 src views, 64 samples/ray, 1000 depth candidates, 24 gaussian"
+RAYS_LIMIT = None                              # --rays: render only the first N rays of the image (per-GPU share of a bigger job)
+
+
+def select_workload(name, rays=None):
+    """Default = BASELINE.json configs[1] (the headline).  'stress1024' = configs[4]: 1024x1024, 8 source views, 256 samples/ray;
+    with --rays 131072 it is the per-GPU share of that image on 8 GPUs.  Not part of the driver contract (default unchanged)."""
+    global H, W, NV, K, G, FLOP_PER_SAMPLE, FLOP_PRE_PER_SAMPLE, WORKLOAD, RAYS_LIMIT
+    if name == "stress1024":
+        H = W = 1024
+        NV, K = 8, 256
+        G = int(15 * K / 40)
+        WORKLOAD = "stress: DTU-shaped synthetic 1024x1024, 8 src views, 256 samples/ray, 1000 depth candidates, %d gaussian" % G
+    elif name != "dtu512":
+        raise SystemExit("unknown --workload %s" % name)
+    FLOP_PER_SAMPLE = 4774912 * NV + 2101248
+    FLOP_PRE_PER_SAMPLE = 4774912 * NV
+    RAYS_LIMIT = rays
+    if rays:
+        WORKLOAD += " (first %d rays of the image)" % rays
 
 
 def peaks():
@@ -89,6 +108,9 @@ def build_inputs():
     mlp = S.make_mlp_state(seed=SEED)
     rays = S.gen_rays(batch["target_extrinsics"], batch["target_intrinsics"], W, H,
                       torch.full((1,), NEAR), torch.full((1,), FAR)).view(1, H * W, 8).contiguous()
+    if RAYS_LIMIT:
+        start = max(0, (H // 2) * W - RAYS_LIMIT // 2)          # rows around the image centre
+        rays = rays[:, start:start + RAYS_LIMIT].contiguous()
     return batch, latent, mlp, rays
 
 
@@ -176,7 +198,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", default=os.environ.get("DINER_B200_MODE", "parity"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="dtu512", help="dtu512 (default, BASELINE configs[1]) | stress1024 (configs[4])")
+    ap.add_argument("--rays", type=int, default=0, help="render only N rays of the image (0 = all)")
     args = ap.parse_args()
+    select_workload(args.workload, args.rays or None)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
         return reference_arm(args)
@@ -196,7 +221,7 @@ def main():
     batch, latent, mlp, rays = build_inputs()
     model = product_model(batch, latent, mlp, dev, args.mode)
     rend = NeRFRendererDGS(n_samples=K, n_depth_candidates=C, n_gaussian=G, white_bkgd=WHITE)
-    n_total = H * W
+    n_total = rays.shape[1]
     per = (n_total + world - 1) // world
     lo, hi = rank * per, min(n_total, (rank + 1) * per)
     from diner_b200.multi_gpu import render_sharded
@@ -282,7 +307,8 @@ def main():
                       "fp32": "f32"}[args.mode],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "mode": args.mode, "rays_per_step": n_total, "sharding": "rays/%d" % world,
-                       "l2": "inputs larger than L2 (2.5 GB fp32 lin_z maps gathered per sample-view, 1 GiB activations scratch per 524288 samples)",
+                       "l2": "inputs larger than L2 (%.1f GB fp32 lin_z maps gathered per sample-view, 1 GiB activations scratch per 524288 samples)"
+                             % (3 * NV * ((H + 128) // 2) * ((W + 128) // 2) * 512 * 4 / 1e9),
                        "cluster": int(os.environ.get("DINER_TC_CLUSTER", "1"))},
             "e2e": {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                     "h2d_bytes_per_step": rays_host.numel() * 4, "d2h_bytes_per_step": (rgb_h.numel() + dep_h.numel()) * 4},
@@ -300,7 +326,7 @@ def main():
                          "stage_ms_per_step": stage,
                          "once_per_scene_ms": {"lin_z_maps (hoisted lin_z over all latent pixels, excluded from the step like the scene encode)": scene_prepare_ms}},
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "dtu512" and not args.rays:
             line["cpu_baseline"] = cpu_baseline(batch, latent, mlp, rays)
             try:
                 del model
