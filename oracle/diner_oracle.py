@@ -347,6 +347,32 @@ def make_scene_state(batch, latent, mlp, feature_padding=32.0, **kw) -> Scene:
                  feature_padding=feature_padding, **kw)
 
 
+def loss_and_grads(scene: Scene, rays, z, gt_rgb, white_bkgd):
+    """Training-step gradients of the hot path (groundwork for BASELINE config 3): the MSE of
+    DINER.calc_losses (src/models/diner.py:259-266, `criterion = MSELoss(reduction="mean")`, :61) on the rendered colours of
+    given sample depths `z` (the sampler is @torch.no_grad in the reference, nerf_renderer.py:65), back-propagated by torch
+    autograd through composite -> PixelNeRF.forward -> ResnetFC to the MLP parameters and the latent maps.
+    Returns (loss, {param name: grad}, d loss / d latent)."""
+    leaf_mlp = {k: v.detach().clone().requires_grad_(True) for k, v in scene.mlp.items()}
+    leaf_lat = scene.latent.detach().clone().requires_grad_(True)
+    old_mlp, old_lat = scene.mlp, scene.latent
+    scene.mlp, scene.latent = leaf_mlp, leaf_lat
+    try:
+        _, rgb, _ = composite(scene, rays, z, white_bkgd)
+        loss = F.mse_loss(rgb, gt_rgb, reduction="mean")
+        loss.backward()
+    finally:
+        scene.mlp, scene.latent = old_mlp, old_lat
+    return loss.detach(), {k: v.grad for k, v in leaf_mlp.items()}, leaf_lat.grad
+
+
+def grad_digest(t, n=256):
+    """Compact, order-sensitive summary of a gradient tensor for a small fixture: L2 norm, sum, and a strided sample."""
+    f = t.detach().reshape(-1).double()
+    idx = (torch.arange(min(n, f.numel())) * max(1, f.numel() // n)) % f.numel()
+    return dict(norm=float(f.norm()), sum=float(f.sum()), sample=f[idx].float().clone(), numel=f.numel())
+
+
 def psnr(pred, gt):
     """-10 log10(mse), data_range 1 (matches reference src/evaluation/eval_suite.py:66)."""
     return float(-10.0 * torch.log10(torch.mean((pred - gt) ** 2)))

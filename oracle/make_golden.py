@@ -132,6 +132,39 @@ def run_reference(ns, cfg, batch, latent, mlp, rays, noise):
                 normals=model.encoder.normals.clone())
 
 
+GRAD_CASE = dict(H=64, W=64, NV=4, SB=1, near=1.0, far=2.5, K=32, C=1000, G=12, white=True, nr=48, seed=1)   # cfg1 inputs, 48 rays
+
+
+def grad_case_inputs():
+    cfg = GRAD_CASE
+    batch, latent, mlp, rays, noise = case_inputs(cfg)
+    gt = S.hash_uniform((cfg["SB"], rays.shape[1], 3), cfg["seed"], 950)
+    return cfg, batch, latent, mlp, rays, noise, gt
+
+
+def make_grad_golden(ns, outdir):
+    """Loss and gradients of the UNMODIFIED reference (autograd through NeRFRendererDGS.composite / PixelNeRF.forward /
+    ResnetFC with the MSE of diner.py:61,266) on the reference's own sample depths: the pin for the backward row."""
+    cfg, batch, latent, mlp, rays, noise, gt = grad_case_inputs()
+    ref = run_reference(ns, cfg, batch, latent, mlp, rays, noise)
+    z = ref["z_filled"]
+    model = build_reference_model(ns, batch, latent, mlp)
+    lat = latent.clone().requires_grad_(True)
+    model.encoder.latent = lat
+    for p in model.parameters():
+        p.requires_grad_(True)
+    rend = ns.nerf_renderer.NeRFRendererDGS(n_samples=cfg["K"], n_depth_candidates=cfg["C"], n_gaussian=cfg["G"],
+                                            white_bkgd=cfg["white"])
+    _, rgb, _ = rend.composite(model, rays, z)
+    loss = torch.nn.MSELoss(reduction="mean")(rgb, gt)
+    loss.backward()
+    grads = {k: O.grad_digest(p.grad) for k, p in model.mlp_fine.named_parameters()}
+    torch.save(dict(cfg=cfg, z=z.contiguous(), loss=float(loss), grads=grads, latent_grad=O.grad_digest(lat.grad, 4096)),
+               os.path.join(outdir, "grads_cfg1_face64.pt"))
+    print("grad golden: loss %.6f, |dL/dlatent| %.4g, |dL/dW(lin_out)| %.4g" % (
+        float(loss), float(lat.grad.norm()), float(model.mlp_fine.lin_out.weight.grad.norm())))
+
+
 GEN_RAYS_CASES = {   # name: H, W, SB, near, far, seed  (caller side of the hot path: src/util/cam_geometry.py:5-48)
     "gen_rays_24x16": dict(H=16, W=24, SB=2, near=1.0, far=2.5, seed=3),
     "gen_rays_64x96": dict(H=64, W=96, SB=2, near=0.3211, far=1.2041, seed=3),
@@ -161,6 +194,9 @@ def main():
     os.makedirs(outdir, exist_ok=True)
     make_gen_rays_golden(ns, outdir)
     if "--rays-only" in sys.argv:
+        return
+    make_grad_golden(ns, outdir)
+    if "--grads-only" in sys.argv:
         return
     for name, cfg in CASES.items():
         batch, latent, mlp, rays, noise = case_inputs(cfg)
