@@ -35,8 +35,20 @@ CASES = {
 }
 
 
+_CASE_CACHE = {}
+
+
 def case_inputs(cfg):
-    """Everything both the reference and the oracle / CUDA path consume, regenerated from the seed."""
+    """Everything both the reference and the oracle / CUDA path consume, regenerated from the seed (memoised per
+    process: the hash-based latent takes seconds to build and many tests share a case; callers must not modify it in place)."""
+    key = tuple(sorted(cfg.items()))
+    if key not in _CASE_CACHE:
+        _CASE_CACHE[key] = _case_inputs(cfg)
+    batch, latent, mlp, rays, noise = _CASE_CACHE[key]
+    return dict(batch), latent, dict(mlp), rays, dict(noise)
+
+
+def _case_inputs(cfg):
     batch = S.make_scene(cfg["H"], cfg["W"], cfg["NV"], cfg["SB"], cfg["near"], cfg["far"], cfg["seed"])
     Hl, Wl = (cfg["H"] + 128) // 2, (cfg["W"] + 128) // 2
     latent = S.make_latent(cfg["SB"], cfg["NV"], 512, Hl, Wl, cfg["seed"])
