@@ -37,6 +37,8 @@ SIGNATURES = {
     "diner_render_image": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
     "diner_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P]),
     "diner_depth2normal": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "diner_render_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "diner_mlp_param_count": (_LL, [_P]),
     "diner_render_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _U64, _P, _P, _P]),
     "diner_sample": (_I, [_P, _P, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
     "diner_query": (_I, [_P, _P, _P, _I, _LL, _I, _P, _P]),
@@ -220,6 +222,19 @@ class Context:
                                                     _ptr(intrinsics, (N, 3, 3), "intrinsics"), N, H, W, _ptr(normals),
                                                     _stream(self.device)))
         return normals
+
+    def render_backward(self, rays, z, white_bkgd, g_rgb, g_depth=None, want_latent_grad=True, latent_shape=None):
+        """EXPERIMENTAL (see include/diner_b200.h): returns (flat parameter gradients in diner_set_mlp order, d_latent NCHW)."""
+        SB, NR, K = z.shape
+        n = int(self.lib.diner_mlp_param_count(self.handle))
+        gp = torch.zeros(n, device=z.device)
+        dl = torch.zeros(latent_shape, device=z.device) if want_latent_grad else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.diner_render_backward(
+                self.handle, _ptr(rays, (SB, NR, 8), "rays"), _ptr(z, name="z"), SB, NR, K, int(bool(white_bkgd)),
+                _ptr(g_rgb, (SB, NR, 3), "g_rgb"), _ptr(g_depth, (SB, NR), "g_depth") if g_depth is not None else None,
+                _ptr(gp), _ptr(dl) if dl is not None else None, _stream(self.device)))
+        return gp, dl
 
     def sample(self, rays, K, C, G, noise=None, want_dgs=False):
         SB, NR, _ = rays.shape

@@ -50,7 +50,7 @@ struct diner_ctx {
     DevBuf mlp_store;                // all fp32 parameters, contiguous
     SceneDev scene{};
     DevBuf latent, maps, cams;       // library-owned scene copies
-    DevBuf zbuf, netbuf, simt_ws, rays_dev, out_dev, rays_img;
+    DevBuf zbuf, netbuf, simt_ws, rays_dev, out_dev, rays_img, bwd_ws, dpre;
     void* host_pin = nullptr; size_t host_pin_cap = 0;
     TcState tc;                      // packed weights + scratch of the tcgen05 path
     long long launches = 0;
@@ -90,7 +90,7 @@ extern "C" void diner_destroy(diner_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     c->mlp_store.release(); c->latent.release(); c->maps.release(); c->cams.release();
-    c->zbuf.release(); c->netbuf.release(); c->simt_ws.release(); c->rays_dev.release(); c->out_dev.release(); c->rays_img.release();
+    c->zbuf.release(); c->netbuf.release(); c->simt_ws.release(); c->rays_dev.release(); c->out_dev.release(); c->rays_img.release(); c->bwd_ws.release(); c->dpre.release();
     tc_release(c->tc);
     if (c->host_pin) cudaFreeHost(c->host_pin);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -358,6 +358,42 @@ extern "C" int diner_render(diner_ctx* c, const float* rays, int SB, int NR, int
     if (!rc) rc = do_composite(c, rays, zz, SB, NR, K, white_bkgd, mode, rgb, depth, weights, st);
     c->launches += g_launches - l0;
     return rc;
+}
+
+extern "C" long long diner_mlp_param_count(diner_ctx* c) {
+    return (c && c->has_mlp) ? (long long)backward_param_count(c->mlp) : 0;
+}
+
+// EXPERIMENTAL (fp32 CUDA cores, not yet validated on hardware): gradients of sum(g_rgb . rgb) + sum(g_depth . depth) through
+// composite -> PixelNeRF.forward -> ResnetFC for given sample depths z.
+extern "C" int diner_render_backward(diner_ctx* c, const float* rays, const float* z, int SB, int NR, int K, int white_bkgd,
+                                     const float* g_rgb, const float* g_depth, float* grad_params, float* d_latent, void* stream) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_render_args(c, SB, NR, K, -1, -1))) return rc;
+    if ((long long)SB * NR == 0) return DINER_OK;
+    if (!rays || !z || !g_rgb || !grad_params) return fail(DINER_E_INVALID, "NULL pointer argument");
+    if (c->scene.L != c->mlp.d_latent) return fail(DINER_E_INVALID, "latent channels %d != d_latent %d", c->scene.L, c->mlp.d_latent);
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long l0 = g_launches;
+    const long long n_rays = (long long)SB * NR, n = n_rays * K;
+    // fp32 forward for the per-sample outputs the compositing derivative needs
+    CUDA_TRY(c->netbuf.reserve((size_t)n * 4 * sizeof(float)));
+    QueryArgs q{};
+    q.SB = SB; q.n_per_sb = (long long)NR * K; q.rays = rays; q.z = z; q.K = K;
+    q.out = c->netbuf.as<float>();
+    rc = run_query(c, q, DINER_MODE_FP32, st);
+    if (rc) return rc;
+    CUDA_TRY(c->dpre.reserve((size_t)n * 4 * sizeof(float)));
+    CUDA_TRY(launch_composite_backward(rays, z, q.out, n_rays, K, white_bkgd, g_rgb, g_depth, c->dpre.as<float>(), st));
+    const long long chunk = 32768;
+    CUDA_TRY(c->bwd_ws.reserve(backward_workspace_bytes(c->mlp, c->scene, chunk)));
+    cudaError_t e = backward_simt(c->scene, c->mlp, q, c->dpre.as<float>(), grad_params, d_latent, c->bwd_ws.as<float>(), chunk, st);
+    c->launches += g_launches - l0;
+    if (e == cudaErrorNotSupported) return fail(DINER_E_UNSUPPORTED, "backward needs >= 1 block before and after combine_layer");
+    if (e != cudaSuccess) return fail(DINER_E_CUDA, "backward_simt: %s", cudaGetErrorString(e));
+    return DINER_OK;
 }
 
 extern "C" int diner_depth2normal(diner_ctx* c, const float* depths, const float* intrinsics, int N, int H, int W, float* normals,

@@ -2,6 +2,7 @@
 #include "scene.cu"
 #include "sampler.cu"
 #include "mlp_simt.cu"
+#include "backward_simt.cu"
 #include "composite.cu"
 #include "mlp_tc.cu"
 #include "mlp_tc2.cu"

@@ -19,6 +19,52 @@ except Exception:                       # same attribute-access contract without
             self[k] = v
 
 
+EXPERIMENTAL_BACKWARD = "DINER_B200_EXPERIMENTAL_BACKWARD"   # =1 enables the (not yet hardware-validated) fp32 backward
+
+
+def mlp_param_order(mlp):
+    """Names of the ResnetFC parameters in libdiner_b200's canonical order (the argument order of diner_set_mlp)."""
+    names = ["lin_in.weight", "lin_in.bias", "lin_out.weight", "lin_out.bias"]
+    for b in range(mlp.n_blocks):
+        names += ["blocks.%d.fc_0.weight" % b, "blocks.%d.fc_0.bias" % b, "blocks.%d.fc_1.weight" % b, "blocks.%d.fc_1.bias" % b]
+    for b in range(min(mlp.combine_layer, mlp.n_blocks)):
+        names += ["lin_z.%d.weight" % b, "lin_z.%d.bias" % b]
+    return names
+
+
+class _RenderWithGrad(torch.autograd.Function):
+    """Training-step path (src/models/diner.py:257-266): forward through the fused kernels, backward through
+    diner_render_backward (EXPERIMENTAL, fp32 CUDA cores).  Gradients reach the ResnetFC parameters and encoder.latent."""
+
+    @staticmethod
+    def forward(ctx, renderer, model, rays, latent, *params):
+        c = model.context()
+        rgb, depth, _, z = c.render(rays, int(renderer.n_samples), int(renderer.n_depth_candidates), int(renderer.n_gaussian),
+                                    renderer.white_bkgd, model.mode_id(), renderer._noise_for_call(), want_z=True)
+        ctx.save_for_backward(rays, z)
+        ctx.model, ctx.white, ctx.latent_shape = model, renderer.white_bkgd, tuple(latent.shape)
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.need_latent = latent.requires_grad
+        return rgb, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth):
+        rays, z = ctx.saved_tensors
+        c = ctx.model.context()
+        gp, dl = c.render_backward(rays, z, ctx.white, g_rgb.float().contiguous(),
+                                   g_depth.float().contiguous() if g_depth is not None else None,
+                                   want_latent_grad=ctx.need_latent, latent_shape=ctx.latent_shape)
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            grads.append(gp[off:off + n].view(shp))
+            off += n
+        assert off == gp.numel()
+        return (None, None, None, dl) + tuple(grads)
+
+
 class NeRFRendererDGS(torch.nn.Module):
     def __init__(self, n_samples=40, n_depth_candidates=1000, n_gaussian=15, eval_batch_size=100000,
                  white_bkgd=True):
@@ -58,6 +104,13 @@ class NeRFRendererDGS(torch.nn.Module):
     def forward(self, model, rays, want_weights=False):
         """rays (SB,B,8) [origin3, dir3, near, far] -> DotMap(fine=DotMap(rgb (SB,B,3), depth (SB,B)[, weights]))."""
         assert len(rays.shape) == 3
+        import os
+        if (torch.is_grad_enabled() and os.environ.get(EXPERIMENTAL_BACKWARD) == "1" and not want_weights and
+                any(p.requires_grad for p in model.mlp_fine.parameters())):
+            named = dict(model.mlp_fine.named_parameters())
+            params = [named[k] for k in mlp_param_order(model.mlp_fine)]
+            rgb, depth = _RenderWithGrad.apply(self, model, rays.float().contiguous(), model.encoder.latent, *params)
+            return DotMap(fine=self._format_outputs(None, rgb, depth, False))
         model._no_grad_only(rays)
         rgb, depth, w, _ = model.context().render(
             rays.float().contiguous(), int(self.n_samples), int(self.n_depth_candidates), int(self.n_gaussian),

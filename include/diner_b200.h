@@ -105,6 +105,18 @@ int diner_gen_rays(diner_ctx* ctx, const float* target_extrinsics, const float* 
 int diner_depth2normal(diner_ctx* ctx, const float* depths, const float* intrinsics, int N, int H, int W, float* normals,
                        void* stream);
 
+/* EXPERIMENTAL -- backward of the render path for the training step (src/models/diner.py:257-266: MSE on the rendered colours,
+ * autograd through NeRFRendererDGS.composite / PixelNeRF.forward / ResnetFC; the sampler is @torch.no_grad).  fp32 CUDA cores,
+ * correctness anchor for a tcgen05 version; NOT yet validated on hardware, the Python modules only use it when
+ * DINER_B200_EXPERIMENTAL_BACKWARD=1.  Given the sample depths z (SB,NR,K) of the forward call and the upstream gradients
+ * g_rgb (SB,NR,3), g_depth (SB,NR) or NULL, ACCUMULATES
+ *   grad_params: diner_mlp_param_count() floats in the order of diner_set_mlp's arguments (lin_in w,b; lin_out w,b; per block
+ *                fc_0 w,b, fc_1 w,b; per lin_z block w,b)
+ *   d_latent:    (SB,NV,L,Hl,Wl) NCHW like the latent passed to diner_set_scene, or NULL. */
+int diner_render_backward(diner_ctx* ctx, const float* rays, const float* z, int SB, int NR, int K, int white_bkgd,
+                          const float* g_rgb, const float* g_depth, float* grad_params, float* d_latent, void* stream);
+long long diner_mlp_param_count(diner_ctx* ctx);
+
 /* Same call with HOST buffers (rays in, rgb/depth out): copies host->device, renders, copies back and
  * synchronises the stream.  This is the end-to-end entry a non-torch caller uses. */
 int diner_render_host(diner_ctx* ctx, const float* rays_host, int SB, int NR, int K, int C, int G,

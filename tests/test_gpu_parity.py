@@ -333,3 +333,38 @@ def test_pair_kernel_pipeline_shape_sweep(NV, SB, K, nr):
     assert e_rgb <= TOL and e_d <= 2 * TOL
     _, rgb_s, _ = ctx.composite(rays, z, True, 2, want_weights=False)       # fast mode runs the same protocol with other timings
     assert bool(torch.isfinite(rgb_s).all()) and float((rgb_s - rgb_f).abs().max()) < 5e-2
+
+
+@pytest.mark.skipif(os.environ.get("DINER_B200_EXPERIMENTAL_BACKWARD") != "1",
+                    reason="experimental fp32 backward (diner_render_backward) is not validated on hardware yet; "
+                           "set DINER_B200_EXPERIMENTAL_BACKWARD=1 to run")
+def test_backward_matches_reference_gradients(golden_dir):
+    """BASELINE config 3 groundwork: diner_render_backward against loss / gradient digests of the UNMODIFIED reference
+    (tests/golden/grads_cfg1_face64.pt, autograd through composite / PixelNeRF.forward / ResnetFC with the MSE of diner.py:266)."""
+    from diner_b200.nerf_renderer import mlp_param_order
+    g = torch.load(os.path.join(golden_dir, "grads_cfg1_face64.pt"))
+    cfg, batch, latent, mlp, rays, noise, gt = MG.grad_case_inputs()
+    model = product_model(batch, latent, mlp, "cuda", "fp32")
+    ctx = model.context()
+    r, z = rays.cuda(), g["z"].cuda().contiguous()
+    _, rgb, _ = ctx.composite(r, z, cfg["white"], 0, want_weights=False)
+    loss = float(((rgb.cpu() - gt) ** 2).mean())
+    assert abs(loss - g["loss"]) <= 1e-5
+    g_rgb = (2.0 * (rgb - gt.cuda()) / rgb.numel()).contiguous()          # d MSE(mean) / d rgb
+    gp, dl = ctx.render_backward(r, z, cfg["white"], g_rgb, None, True, tuple(latent.shape))
+    named = dict(model.mlp_fine.named_parameters())
+    off = 0
+
+    def check(name, t, ref, n):
+        d = O.grad_digest(t.cpu(), n)
+        assert d["numel"] == ref["numel"], name
+        assert abs(d["norm"] - ref["norm"]) <= 2e-3 * ref["norm"], (name, d["norm"], ref["norm"])
+        scale = float(ref["sample"].abs().max().clamp_min(1e-12))
+        assert float((d["sample"] - ref["sample"]).abs().max()) / scale <= 5e-3, name
+
+    for k in mlp_param_order(model.mlp_fine):
+        n = named[k].numel()
+        check(k, gp[off:off + n], g["grads"][k], 256)
+        off += n
+    assert off == gp.numel()
+    check("latent", dl, g["latent_grad"], 4096)
