@@ -364,7 +364,7 @@ extern "C" long long diner_mlp_param_count(diner_ctx* c) {
     return (c && c->has_mlp) ? (long long)backward_param_count(c->mlp) : 0;
 }
 
-// EXPERIMENTAL (fp32 CUDA cores, not yet validated on hardware): gradients of sum(g_rgb . rgb) + sum(g_depth . depth) through
+// EXPERIMENTAL (fp32 CUDA cores; one passing hardware run against the reference gradients so far): gradients of sum(g_rgb . rgb) + sum(g_depth . depth) through
 // composite -> PixelNeRF.forward -> ResnetFC for given sample depths z.
 extern "C" int diner_render_backward(diner_ctx* c, const float* rays, const float* z, int SB, int NR, int K, int white_bkgd,
                                      const float* g_rgb, const float* g_depth, float* grad_params, float* d_latent, void* stream) {

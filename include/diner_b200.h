@@ -107,7 +107,8 @@ int diner_depth2normal(diner_ctx* ctx, const float* depths, const float* intrins
 
 /* EXPERIMENTAL -- backward of the render path for the training step (src/models/diner.py:257-266: MSE on the rendered colours,
  * autograd through NeRFRendererDGS.composite / PixelNeRF.forward / ResnetFC; the sampler is @torch.no_grad).  fp32 CUDA cores,
- * correctness anchor for a tcgen05 version; NOT yet validated on hardware, the Python modules only use it when
+ * correctness anchor for a tcgen05 version; one passing hardware run against the reference's gradients so far
+ * (tests/test_gpu_parity.py::test_backward_matches_reference_gradients), so the Python modules only use it when
  * DINER_B200_EXPERIMENTAL_BACKWARD=1.  Given the sample depths z (SB,NR,K) of the forward call and the upstream gradients
  * g_rgb (SB,NR,3), g_depth (SB,NR) or NULL, ACCUMULATES
  *   grad_params: diner_mlp_param_count() floats in the order of diner_set_mlp's arguments (lin_in w,b; lin_out w,b; per block
