@@ -107,7 +107,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ A, 
     const long long r_begin = (long long)blockIdx.z * rows_per_split;
     const long long r_end = r_begin + rows_per_split < rows ? r_begin + rows_per_split : rows;
     float acc[4][4] = {};
-    float bsum = 0.0f;      // threads with ty == 0 of the CTAs with blockIdx.y == 0 carry 4 bias columns in turn (see below)
+    float bsum = 0.0f;      // bias gradient: thread c < 64 of the CTAs with blockIdx.y == 0 sums column o0 + c of G over this row slice
     for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
         for (int t = threadIdx.x; t < 16 * 64; t += 256) {
             const int rr = t >> 6, cc = t & 63;

@@ -94,14 +94,20 @@ def manual_backward(scene, rays, z, g_rgb, white):
     return grads, d_lat.permute(0, 2, 1).reshape(SBn, NVn, L, Hl, Wl)
 
 
-def test_manual_backward_chain_matches_autograd():
-    cfg = dict(H=32, W=32, NV=4, SB=1, near=1.0, far=2.5, K=16, C=100, G=6, white=True, nr=24, seed=31)
+import pytest
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(H=32, W=32, NV=4, SB=1, near=1.0, far=2.5, K=16, C=100, G=6, white=True, nr=24, seed=31),
+    dict(H=32, W=48, NV=2, SB=2, near=1.0, far=2.5, K=12, C=100, G=4, white=False, nr=16, seed=32),
+], ids=["nv4_white", "sb2_nv2_black"])
+def test_manual_backward_chain_matches_autograd(cfg):
     batch, latent, mlp, rays, noise = MG.case_inputs(cfg)
     scene = O.make_scene_state(batch, latent, mlp)
     z = O.fill_up_uniform(O.sample_depthguided(scene, rays, cfg["K"], cfg["C"], cfg["G"], noise["u_coarse"], noise["g_noise"]),
                           rays, noise["u_fill"])
     from diner_b200 import synthetic as S
-    gt = S.hash_uniform((1, rays.shape[1], 3), 31, 950)
+    gt = S.hash_uniform((cfg["SB"], rays.shape[1], 3), cfg["seed"], 950)
     loss, g_ref, lat_ref = O.loss_and_grads(scene, rays, z, gt, cfg["white"])
     with torch.no_grad():
         _, rgb, _ = O.composite(scene, rays, z, cfg["white"])

@@ -368,3 +368,68 @@ def test_backward_matches_reference_gradients(golden_dir):
         off += n
     assert off == gp.numel()
     check("latent", dl, g["latent_grad"], 4096)
+
+
+_BWD_GATED = pytest.mark.skipif(os.environ.get("DINER_B200_EXPERIMENTAL_BACKWARD") != "1",
+                                reason="experimental fp32 backward: set DINER_B200_EXPERIMENTAL_BACKWARD=1 to run")
+
+
+@_BWD_GATED
+@pytest.mark.parametrize("cfg", [
+    dict(H=32, W=48, NV=2, SB=2, near=1.0, far=2.5, K=12, C=100, G=4, white=False, nr=40, seed=32),
+    dict(H=32, W=32, NV=8, SB=1, near=1.0, far=2.5, K=16, C=100, G=5, white=True, nr=64, seed=33),
+], ids=["sb2_nv2_black", "nv8_white"])
+def test_backward_other_shapes_vs_oracle_autograd(cfg):
+    """diner_render_backward (with a depth term as well) against torch autograd through the CPU oracle (pinned to the reference's
+    gradients by tests/test_oracle.py) on shapes the golden does not cover: SB > 1, NV != 4, black background."""
+    from diner_b200 import synthetic as S
+    from diner_b200.nerf_renderer import mlp_param_order
+    batch, latent, mlp, rays, noise = MG.case_inputs(cfg)
+    scene = O.make_scene_state(batch, latent, mlp)
+    z = O.fill_up_uniform(O.sample_depthguided(scene, rays, cfg["K"], cfg["C"], cfg["G"], noise["u_coarse"], noise["g_noise"]),
+                          rays, noise["u_fill"])
+    g_rgb = S.hash_normal((cfg["SB"], rays.shape[1], 3), cfg["seed"], 951) * 0.01
+    g_dep = S.hash_normal((cfg["SB"], rays.shape[1]), cfg["seed"], 952) * 0.01
+    # reference gradients of L = sum(g_rgb * rgb) + sum(g_dep * depth) by autograd through the oracle
+    leaf_mlp = {k: v.clone().requires_grad_(True) for k, v in mlp.items()}
+    leaf_lat = latent.clone().requires_grad_(True)
+    scene.mlp, scene.latent = leaf_mlp, leaf_lat
+    _, rgb, depth = O.composite(scene, rays, z, cfg["white"])
+    ((rgb * g_rgb).sum() + (depth * g_dep).sum()).backward()
+    model = product_model(batch, latent, mlp, "cuda", "fp32")
+    gp, dl = model.context().render_backward(rays.cuda(), z.cuda().contiguous(), cfg["white"], g_rgb.cuda().contiguous(),
+                                             g_dep.cuda().contiguous(), True, tuple(latent.shape))
+    off = 0
+    for k in mlp_param_order(model.mlp_fine):
+        ref = leaf_mlp[k].grad
+        got = gp[off:off + ref.numel()].view(ref.shape).cpu()
+        off += ref.numel()
+        scale = float(ref.abs().max().clamp_min(1e-12))
+        assert float((got - ref).abs().max()) / scale <= 5e-3, (k, float((got - ref).abs().max()), scale)
+    assert off == gp.numel()
+    scale = float(leaf_lat.grad.abs().max())
+    assert scale > 0 and float((dl.cpu() - leaf_lat.grad).abs().max()) / scale <= 5e-3
+
+
+@_BWD_GATED
+def test_training_step_through_module_api(golden_dir):
+    """The module-level path a training step takes (diner.py:257-266): NeRFRendererDGS.forward with grad enabled ->
+    autograd Function -> loss.backward() fills .grad of the ResnetFC parameters and of encoder.latent."""
+    g = torch.load(os.path.join(golden_dir, "grads_cfg1_face64.pt"))
+    cfg, batch, latent, mlp, rays, noise, gt = MG.grad_case_inputs()
+    model = product_model(batch, latent, mlp, "cuda", "fp32").train()
+    model.encoder.latent = model.encoder.latent.detach().clone().requires_grad_(True)
+    model.encoder.scene_version += 1
+    rend = renderer_for(cfg, noise)
+    out = rend(model, rays.cuda())
+    loss = torch.nn.functional.mse_loss(out.fine.rgb, gt.cuda())
+    loss.backward()
+    # same noise -> same sample depths as the golden (well-conditioned rays; a flipped shortlist entry would only move the
+    # loss slightly), so the loss and the gradient norms must be close to the reference's
+    assert abs(float(loss) - g["loss"]) <= 2e-3
+    for k, p in model.mlp_fine.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+        ref = g["grads"][k]["norm"]
+        assert abs(float(p.grad.double().norm()) - ref) <= 0.05 * ref + 1e-9, (k, float(p.grad.norm()), ref)
+    lg = model.encoder.latent.grad
+    assert lg is not None and abs(float(lg.double().norm()) - g["latent_grad"]["norm"]) <= 0.05 * g["latent_grad"]["norm"]
