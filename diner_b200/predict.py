@@ -21,3 +21,23 @@ def predict_imgs_from_batch(nerf, renderer, batch, znear, zfar, return_depth=Fal
     rgb = rgb.view(SB, H, W, 3).permute(0, 3, 1, 2)
     depth = depth.view(SB, H, W, 1).permute(0, 3, 1, 2)
     return (rgb, depth) if return_depth else rgb
+
+
+def calc_losses(nerf, renderer, batch, znear, zfar, ray_batch_size, generator=None, encode=True):
+    """Training-step loss of the reference (src/models/diner.py:217-290) for w_vgg = w_antibias = 0: random pixels of the target
+    view(s) (`torch.randint`, :232), their rays through NeRFRendererDGS.forward, MSE against the target colours (:259-266).
+    Gradients need the experimental backward (DINER_B200_EXPERIMENTAL_BACKWARD=1, see nerf_renderer.py); the perceptual /
+    anti-bias terms of the reference operate on the rendered patch afterwards and stay in PyTorch."""
+    SB, _, H, W = batch["target_rgb"].shape
+    if encode:
+        encode_batch(nerf, batch)
+    dev = batch["target_rgb"].device
+    rays = nerf.context().gen_rays(batch["target_extrinsics"].float().contiguous(), batch["target_intrinsics"].float().contiguous(),
+                                   H, W, znear, zfar)                                      # (SB, H*W, 8)
+    pix = torch.randint(0, H * W, (SB, ray_batch_size), generator=generator).to(dev)
+    bidx = torch.arange(SB, device=dev).unsqueeze(-1).expand(-1, ray_batch_size)
+    rays = rays[bidx, pix].contiguous()                                                     # (SB, B, 8)
+    pred = renderer(nerf, rays).fine.rgb
+    gt = batch["target_rgb"].view(SB, 3, -1).permute(0, 2, 1)[bidx, pix]                    # (SB, B, 3)
+    loss = torch.nn.functional.mse_loss(pred, gt, reduction="mean")
+    return dict(rgb_fine=loss, vgg_fine=0.0, antibias=0.0, total=loss)

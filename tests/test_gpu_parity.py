@@ -433,3 +433,27 @@ def test_training_step_through_module_api(golden_dir):
         assert abs(float(p.grad.double().norm()) - ref) <= 0.05 * ref + 1e-9, (k, float(p.grad.norm()), ref)
     lg = model.encoder.latent.grad
     assert lg is not None and abs(float(lg.double().norm()) - g["latent_grad"]["norm"]) <= 0.05 * g["latent_grad"]["norm"]
+
+
+@_BWD_GATED
+def test_training_steps_reduce_the_loss():
+    """A few Adam steps (diner.py:333) through calc_losses on a fixed tiny scene must reduce the MSE."""
+    from diner_b200 import synthetic as S
+    from diner_b200.predict import calc_losses
+    cfg = dict(H=32, W=32, NV=4, SB=1, near=1.0, far=2.5, K=16, C=100, G=6, white=True, nr=16, seed=41)
+    batch, latent, mlp, _, _ = MG.case_inputs(cfg)
+    model = product_model(batch, latent, mlp, "cuda", "fp32").train()
+    rend = renderer_for(cfg)
+    rend.noise = dict(seed=3)
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    b["target_rgb"] = S.hash_uniform((1, 3, 32, 32), 41, 960).cuda()
+    opt = torch.optim.Adam(model.mlp_fine.parameters(), lr=1e-4)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        out = calc_losses(model, rend, b, cfg["near"], cfg["far"], 256, generator=torch.Generator().manual_seed(0), encode=False)
+        out["total"].backward()
+        opt.step()
+        losses.append(float(out["total"]))
+    print("training losses:", ["%.5f" % v for v in losses])
+    assert losses[-1] < losses[0]
