@@ -171,6 +171,8 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm is a CPU measurement on all host cores
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     batch, latent, mlp, rays = build_inputs()
     n_rays = 4096
     vals = []
