@@ -192,6 +192,59 @@ def reference_arm(args):
                       "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def train_bench(args):
+    """BASELINE.json configs[2] (NOT part of the driver contract; needs DINER_B200_EXPERIMENTAL_BACKWARD=1): Facescape-shaped
+    training step -- SB=4 scenes of 256x256, 4 source views, 128 samples/ray, 4096 random rays per scene (ray_batch_size,
+    diner.py:57), MSE loss, backward through the renderer to the ResnetFC parameters and the latent maps, Adam step
+    (diner.py:333).  Forward in --mode, backward on fp32 CUDA cores (csrc/backward_simt.cu).  Single GPU."""
+    os.environ.setdefault("DINER_B200_EXPERIMENTAL_BACKWARD", "1")
+    from diner_b200 import synthetic as S
+    from diner_b200.nerf_renderer import NeRFRendererDGS
+    from diner_b200.predict import calc_losses
+    from tests.common import product_model
+    Ht = Wt = 256
+    SBt, NVt, Kt, RB = 4, 4, 128, 4096
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    batch = S.make_scene(Ht, Wt, NVt, SBt, 1.0, 2.5, SEED)
+    gen = torch.Generator().manual_seed(SEED)
+    latent = torch.randn(SBt, NVt, 512, (Ht + 128) // 2, (Wt + 128) // 2, generator=gen) * 0.5
+    model = product_model(batch, latent, S.make_mlp_state(seed=SEED), dev, args.mode).train()
+    model.encoder.latent = model.encoder.latent.detach().clone().requires_grad_(True)
+    model.encoder.scene_version += 1
+    rend = NeRFRendererDGS(n_samples=Kt, n_depth_candidates=C, n_gaussian=int(15 * Kt / 40), white_bkgd=True)
+    b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    b["target_rgb"] = torch.rand(SBt, 3, Ht, Wt, generator=gen).to(dev)
+    opt = torch.optim.Adam(list(model.mlp_fine.parameters()) + [model.encoder.latent], lr=1e-4)
+    g = torch.Generator().manual_seed(1)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = calc_losses(model, rend, b, 1.0, 2.5, RB, generator=g, encode=False)["total"]
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    rays_step = SBt * RB
+    flop = 3 * rays_step * Kt * (4774912 * NVt + 2101248)          # forward + ~2x for dgrad + wgrad
+    print(json.dumps({"metric": "train_rays_per_sec", "value": rays_step / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "forward %s, backward f32 CUDA cores (experimental)" % args.mode, "data": "synthetic",
+                      "config": {"workload": "Facescape-shaped synthetic training step: SB=4 x 256x256, 4 src views, 128 samples/ray, "
+                                             "4096 rays/scene, MSE + backward + Adam", "mode": args.mode},
+                      "loss": float(loss), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,9 +253,11 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", default=os.environ.get("DINER_B200_MODE", "parity"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="dtu512", help="dtu512 (default, BASELINE configs[1]) | stress1024 (configs[4])")
+    ap.add_argument("--workload", default="dtu512", help="dtu512 (default, BASELINE configs[1]) | stress1024 (configs[4]) | train256 (configs[2], experimental backward)")
     ap.add_argument("--rays", type=int, default=0, help="render only N rays of the image (0 = all)")
     args = ap.parse_args()
+    if args.workload == "train256":
+        return train_bench(args)
     select_workload(args.workload, args.rays or None)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
