@@ -90,7 +90,7 @@ class PixelNeRF(torch.nn.Module):
         enc = self.encoder
         if enc.nviews is None:
             raise RuntimeError("PixelNeRF.encode() must be called before rendering")
-        sstamp = (enc.scene_version, enc.latent.data_ptr(), self.poses.data_ptr(), self.poses._version)
+        sstamp = (enc.scene_version, enc.latent.data_ptr(), enc.latent._version, self.poses.data_ptr(), self.poses._version)
         if sstamp != self._scene_stamp:
             if enc.index_interp != "bilinear" or enc.index_padding != "border":
                 raise NotImplementedError("libdiner_b200 implements bilinear/border latent indexing only")
