@@ -107,3 +107,18 @@ def test_leaf_modules_match_oracle():
     sc = O.Scene(*([None] * 8), mlp=sd)
     with torch.no_grad():
         assert torch.allclose(net(zx, combine_dim=1), O.resnetfc(sc, zx), atol=1e-6)
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every ctypes prototype in diner_b200/capi.py has as many arguments as the declaration in include/diner_b200.h
+    (a mismatch would corrupt the call silently: ctypes does not check arity against the binary)."""
+    from diner_b200 import capi
+    header = open(os.path.join(ROOT, "include", "diner_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decls = dict(re.findall(r"\b(diner_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert set(decls) == set(capi.SIGNATURES)
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(capi.SIGNATURES[name][1]), "%s: header has %d parameters, ctypes table %d" % (
+            name, n, len(capi.SIGNATURES[name][1]))
