@@ -35,6 +35,13 @@ CASES = {
 }
 
 
+# Oracle-only pins at the sample counts of BASELINE configs[2] / configs[4] (not in CASES: the GPU parity tests iterate CASES,
+# and a new GPU case has to be validated on hardware before it may gate a round)
+EXTRA_CASES = {
+    "k128_sb2_face": dict(H=64, W=64, NV=4, SB=2, near=1.0, far=2.5, K=128, C=1000, G=48, white=True, nr=24, seed=6),
+    "k256_nv8": dict(H=64, W=64, NV=8, SB=1, near=1.0, far=2.5, K=256, C=1000, G=96, white=False, nr=24, seed=7),
+}
+
 _CASE_CACHE = {}
 
 
@@ -207,10 +214,12 @@ def main():
     make_gen_rays_golden(ns, outdir)
     if "--rays-only" in sys.argv:
         return
-    make_grad_golden(ns, outdir)
+    if "--extra-only" not in sys.argv:
+        make_grad_golden(ns, outdir)
     if "--grads-only" in sys.argv:
         return
-    for name, cfg in CASES.items():
+    todo = dict(EXTRA_CASES) if "--extra-only" in sys.argv else dict(CASES, **EXTRA_CASES)
+    for name, cfg in todo.items():
         batch, latent, mlp, rays, noise = case_inputs(cfg)
         ref = run_reference(ns, cfg, batch, latent, mlp, rays, noise)
         pix_alpha = ref["weights"].sum(-1)
