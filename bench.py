@@ -193,15 +193,14 @@ def reference_arm(args):
 
 
 def train_bench(args):
-    """BASELINE.json configs[2] (NOT part of the driver contract; needs DINER_B200_EXPERIMENTAL_BACKWARD=1): Facescape-shaped
+    """BASELINE.json configs[2] (NOT part of the driver contract): Facescape-shaped
     training step -- SB=4 scenes of 256x256, 4 source views, 128 samples/ray, 4096 random rays per scene (ray_batch_size,
     diner.py:57), MSE loss, backward through the renderer to the ResnetFC parameters and the latent maps, Adam step
     (diner.py:333).  Forward in --mode, backward on fp32 CUDA cores (csrc/backward_simt.cu).  Single GPU."""
-    os.environ.setdefault("DINER_B200_EXPERIMENTAL_BACKWARD", "1")
     from diner_b200 import synthetic as S
     from diner_b200.nerf_renderer import NeRFRendererDGS
     from diner_b200.predict import calc_losses
-    from tests.common import product_model
+    from diner_b200.synthetic import product_model
     Ht = Wt = 256
     SBt, NVt, Kt, RB = 4, 4, 128, 4096
     dev = torch.device("cuda", 0)
@@ -245,6 +244,45 @@ def train_bench(args):
                       "loss": float(loss), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12}))
 
 
+def latest_traffic():
+    """dram bytes per PRE launch from the newest committed ncu --set full summary (profiles/*_traffic.json, written by
+    tools/ncu_summary.py from the .ncu-rep of the same kernel); None when there is none."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+        try:
+            d = json.load(open(f))
+            best = dict(d, file=os.path.relpath(f, ROOT))
+        except Exception:
+            pass
+    return best
+
+
+def parity_check(model, rend_cfg, batch, latent, mlp, rays, dev, n_rays=2048):
+    """Rendered output of the CUDA path vs the oracle (torch-CPU port pinned to the reference) on a bounded strided sample of
+    the workload's rays, outside every timed region: stage-wise on the oracle's own sample depths (max |err| over all rays,
+    the 1e-4 bar) and end to end with the same injected noise (PSNR; rays beyond 1e-4 come from erf-ulp shortlist flips
+    between torch-CPU and CUDA, tests/test_gpu_parity.py)."""
+    from oracle import diner_oracle as O
+    from diner_b200 import synthetic as S
+    scene = O.make_scene_state(batch, latent, mlp)
+    r = rays[:, strided_pick(n_rays)].contiguous()
+    noise = dict(u_coarse=S.hash_uniform((1, n_rays, C), 1, 1), g_noise=S.hash_normal((1, n_rays, G), 1, 2),
+                 u_fill=S.hash_uniform((1, n_rays, K), 1, 3))
+    with torch.no_grad():
+        rgb_o, dep_o, _, z_o = O.render(scene, r, K, C, G, WHITE, noise["u_coarse"], noise["g_noise"], noise["u_fill"], return_z=True)
+        ctx = model.context()
+        _, rgb_s, dep_s = ctx.composite(r.to(dev), z_o.to(dev).contiguous(), WHITE, model.mode_id(), want_weights=False)
+        rgb_e, dep_e, _, _ = ctx.render(r.to(dev), K, C, G, WHITE, model.mode_id(), {k: v.to(dev).contiguous() for k, v in noise.items()})
+    e_rgb, e_dep = float((rgb_s.cpu() - rgb_o).abs().max()), float((dep_s.cpu() - dep_o).abs().max())
+    e2e = torch.maximum((rgb_e.cpu() - rgb_o).abs().max(-1).values, (dep_e.cpu() - dep_o).abs())
+    return {"rays": n_rays, "reference": "oracle/diner_oracle.py on torch-CPU (pinned to the reference's goldens)",
+            "max_abs_err_rgb": e_rgb, "max_abs_err_depth": e_dep, "psnr_vs_ref_db": O.psnr(rgb_s.cpu(), rgb_o),
+            "stage": "given the oracle's sample depths (every ray)",
+            "end_to_end": {"psnr_vs_ref_db": O.psnr(rgb_e.cpu(), rgb_o), "median_abs_err": float(e2e.median()),
+                           "frac_rays_beyond_1e-4": float((~(e2e <= 1e-4)).float().mean())}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,7 +291,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", default=os.environ.get("DINER_B200_MODE", "parity"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="dtu512", help="dtu512 (default, BASELINE configs[1]) | stress1024 (configs[4]) | train256 (configs[2], experimental backward)")
+    ap.add_argument("--workload", default="dtu512", help="dtu512 (default, BASELINE configs[1]) | stress1024 (configs[4]) | train256 (configs[2])")
     ap.add_argument("--rays", type=int, default=0, help="render only N rays of the image (0 = all)")
     args = ap.parse_args()
     if args.workload == "train256":
@@ -273,7 +311,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
 
-    from tests.common import product_model
+    from diner_b200.synthetic import product_model
     from diner_b200.nerf_renderer import NeRFRendererDGS
     batch, latent, mlp, rays = build_inputs()
     model = product_model(batch, latent, mlp, dev, args.mode)
@@ -286,13 +324,11 @@ def main():
     rays_dev = rays_host.to(dev)
     ctx = model.context()
 
-    def local_render(r):
-        with torch.no_grad():
-            o = rend(model, r)
-        return o.fine.rgb, o.fine.depth
+    def packed_render(r, out):
+        rend.render_packed(model, r, out=out)           # compositing kernel writes rgb|depth into the gather slice
 
     def step(src):
-        return render_sharded(local_render, src)        # one NCCL all-gather of rgb|depth per image when world > 1
+        return render_sharded(packed_render, src, packed=True, return_packed=True)   # one in-place NCCL all-gather per image when world > 1
 
     def sync():
         if world > 1:
@@ -314,16 +350,20 @@ def main():
     sync()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
-    # end-to-end: pinned host rays in, rgb + depth back on the host, every step
+    # end-to-end: host rays in, rgb + depth back on the host, every step.  One GPU: through the C-ABI host-buffer entry
+    # (diner_render_host: H2D copy, render, D2H copies and the stream sync inside the call).  N GPUs: pinned host rays -> device,
+    # sharded render + all-gather, packed image back to the host.
     rgb_h = torch.empty(1, n_total, 3).pin_memory()
     dep_h = torch.empty(1, n_total).pin_memory()
+    img_h = torch.empty(1, n_total, 4).pin_memory()
     sync()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rgb_d, dep_d = step(rays_host.to(dev, non_blocking=True))
-        rgb_h.copy_(rgb_d, non_blocking=True)
-        dep_h.copy_(dep_d, non_blocking=True)
-        torch.cuda.synchronize()
+    for i in range(args.steps):
+        if world == 1:
+            ctx.render_host(rays_host, K, C, G, WHITE, model.mode_id(), 1000 + i, rgb_h, dep_h)
+        else:
+            img_h.copy_(step(rays_host.to(dev, non_blocking=True)), non_blocking=True)
+            torch.cuda.synchronize()
     sync()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     clk = clocks.stop() if rank == 0 else None
@@ -332,7 +372,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    # per-kernel breakdown for the roofline: a separate short pass with CUDA-event timing inside the library
+    # per-kernel breakdown for the roofline: a separate short pass with CUDA-event timing inside the library (events are
+    # recorded on the stream the kernels are launched on)
     ctx.set_timing(True)
     stage = {"sampler": 0.0, "mlp_pre": 0.0, "mlp_post": 0.0, "composite": 0.0}
     nt = 2
@@ -356,33 +397,42 @@ def main():
         pre_ms_per_launch = stage["mlp_pre"] / n_pre_launches if stage["mlp_pre"] > 0 else None
         pre_flops_per_launch = FLOP_PRE_PER_SAMPLE * n_samp_rank / n_pre_launches
         achieved = pre_flops_per_launch / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
+        # FLOPs the PRE kernel actually issues to the tensor pipe per sample-view: lin_in + 3 x (fc_0 + fc_1) (lin_z is hoisted
+        # into the once-per-scene Y maps), x3 MMAs per product in parity mode
+        exec_per_sv = (2 * 64 * 512 + 6 * 2 * 512 * 512) * (3 if args.mode == "parity" else 1)
+        executed = exec_per_sv * NV * n_samp_rank / n_pre_launches / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
+        tr = latest_traffic() if args.mode == "parity" else None
+        e2e_d2h = (rgb_h.numel() + dep_h.numel()) * 4 if world == 1 else img_h.numel() * 4
         line = {
             "metric": "rays_per_sec", "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": {"parity": "bf16x3-split operands, f32 accumulate (1e-4 parity mode)", "fast": "bf16, f32 accumulate",
+            "dtype": {"parity": "f16x3 (fp16 hi/lo split operands, f32 accumulate: the 1e-4 parity mode)", "fast": "f16, f32 accumulate",
                       "fp32": "f32"}[args.mode],
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "mode": args.mode, "rays_per_step": n_total, "sharding": "rays/%d" % world,
-                       "l2": "inputs larger than L2 (%.1f GB fp32 lin_z maps gathered per sample-view, 1 GiB activations scratch per 524288 samples)"
-                             % (3 * NV * ((H + 128) // 2) * ((W + 128) // 2) * 512 * 4 / 1e9),
-                       "cluster": int(os.environ.get("DINER_TC_CLUSTER", "1"))},
+            "config": {"workload": WORKLOAD},
+            "run": {"mode": args.mode, "rays_per_step": n_total, "sharding": "rays/%d" % world,
+                    "l2": "inputs larger than L2 (%.1f GB fp32 lin_z maps gathered per sample-view, 1 GiB activations scratch per 524288 samples)"
+                          % (3 * NV * ((H + 128) // 2) * ((W + 128) // 2) * 512 * 4 / 1e9),
+                    "tail_kb": int(os.environ.get("DINER_TC_TAIL_KB", "-1")),
+                    "e2e_path": "diner_render_host (C ABI, host buffers)" if world == 1 else "pinned host rays -> sharded render + all-gather -> host image"},
             "e2e": {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
-                    "h2d_bytes_per_step": rays_host.numel() * 4, "d2h_bytes_per_step": (rgb_h.numel() + dep_h.numel()) * 4},
+                    "h2d_bytes_per_step": rays_host.numel() * 4, "d2h_bytes_per_step": e2e_d2h},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "tc2::mlp_pair_kernel<PRE> (per sample-view ResnetFC layers; algorithmic FLOPs incl. the hoisted lin_z)",
+            "roofline": {"bound": "tensor", "kernel": "tc2::mlp_pair_kernel<PRE> (per sample-view ResnetFC layers; algorithmic FLOPs per SURVEY 8(d), incl. the hoisted lin_z)",
                          "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["sustained"], "peak_source": pk["src"] + " bf16 dense sustained",
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one PRE launch (524 288 samples) from the ncu --set full
-                         # capture summarised in profiles/r1d_ncu_mlp_pair.md (parity mode); not re-measured by this run
-                         "traffic": 2.998e9 if args.mode == "parity" else None,
-                         "traffic_source": "ncu --set full, profiles/r1d_ncu_mlp_pair.md (bytes per PRE launch)",
+                         "frac": achieved / pk["sustained"], "peak_source": pk["src"] + " bf16 dense sustained (fp16 runs at the same rate)",
+                         "achieved_executed_mma": executed,
+                         "executed_note": "tensor-pipe FLOP/s the kernel really issues (lin_z hoisted out, x3 passes in parity mode); burst peak %.1f" % pk["burst"],
+                         "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                         "traffic_source": ("ncu --set full, %s" % tr["file"]) if tr else None,
                          "whole_step_frac": rays_per_s / world * K * FLOP_PER_SAMPLE / 1e12 / pk["sustained"],
-                         "executed_flop_multiplier": 3 if args.mode == "parity" else 1,
                          "stage_ms_per_step": stage,
                          "once_per_scene_ms": {"lin_z_maps (hoisted lin_z over all latent pixels, excluded from the step like the scene encode)": scene_prepare_ms}},
         }
+        if world == 1 and args.workload == "dtu512" and not args.rays:
+            line["parity"] = parity_check(model, None, batch, latent, mlp, rays, dev)
         if not args.no_cpu_baseline and world == 1 and args.workload == "dtu512" and not args.rays:
             line["cpu_baseline"] = cpu_baseline(batch, latent, mlp, rays)
             try:

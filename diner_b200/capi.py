@@ -34,6 +34,7 @@ SIGNATURES = {
     "diner_set_mlp": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _PP, _PP, _PP, _PP, _PP, _PP, _P]),
     "diner_set_scene": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _P]),
     "diner_render": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P, _P, _P]),
+    "diner_render_rgbd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P]),
     "diner_render_image": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _I, _I, ctypes.POINTER(DinerNoise), _P, _P, _P]),
     "diner_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P, _P]),
     "diner_depth2normal": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -103,7 +104,7 @@ class Context:
         self._check(self.lib.diner_create(ctypes.byref(h), idx))
         self.handle = h
         self._keep = []
-        for key, env in (("cluster", "DINER_TC_CLUSTER"), ("sub_batch", "DINER_TC_SUB_BATCH"), ("kernel", "DINER_TC_KERNEL"),
+        for key, env in (("tail_kb", "DINER_TC_TAIL_KB"), ("sub_batch", "DINER_TC_SUB_BATCH"),
                          ("dbg_skip", "DINER_TC_DBG_SKIP"), ("early_split", "DINER_TC_EARLY_SPLIT")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))
@@ -186,6 +187,19 @@ class Context:
                 _stream(self.device)))
         return rgb, depth, w, z
 
+    def render_rgbd(self, rays, K, C, G, white_bkgd, mode, noise=None, out=None):
+        """diner_render_rgbd: rays (SB,NR,8) -> packed (SB,NR,4) [r,g,b,depth]; `out` may be a contiguous (SB,NR,4) view of a
+        larger buffer (the rank's slice of the image all-gather)."""
+        SB, NR, _ = rays.shape
+        if out is None:
+            out = torch.empty(SB, NR, 4, device=rays.device)
+        n, keep = self._noise(noise, SB, NR, K, C, G)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.diner_render_rgbd(
+                self.handle, _ptr(rays, (SB, NR, 8), "rays"), SB, NR, K, C, G, int(bool(white_bkgd)), mode,
+                ctypes.byref(n) if n is not None else None, _ptr(out, (SB, NR, 4), "rgbd"), _stream(self.device)))
+        return out
+
     def render_image(self, target_extrinsics, target_intrinsics, H, W, z_near, z_far, K, C, G, white_bkgd, mode, noise=None):
         """gen_rays + the ray-batch loop of DINER.predict_imgs_from_batch (diner.py:79-92) in one library call.
         Returns rgb (SB,H*W,3), depth (SB,H*W); noise may only carry a seed (dense noise is per ray batch)."""
@@ -224,7 +238,7 @@ class Context:
         return normals
 
     def render_backward(self, rays, z, white_bkgd, g_rgb, g_depth=None, want_latent_grad=True, latent_shape=None):
-        """EXPERIMENTAL (see include/diner_b200.h): returns (flat parameter gradients in diner_set_mlp order, d_latent NCHW)."""
+        """diner_render_backward (see include/diner_b200.h): returns (flat parameter gradients in diner_set_mlp order, d_latent NCHW)."""
         SB, NR, K = z.shape
         n = int(self.lib.diner_mlp_param_count(self.handle))
         gp = torch.zeros(n, device=z.device)

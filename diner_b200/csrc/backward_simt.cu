@@ -1,7 +1,5 @@
-// Backward pass of the render path on fp32 CUDA cores -- EXPERIMENTAL correctness anchor for BASELINE config 3
-// (training step: loss + backward through the renderer).  One passing hardware run against the reference's gradients so far
-// (tests/test_gpu_parity.py::test_backward_matches_reference_gradients), hence not wired into the default module path yet
-// (diner_b200/nerf_renderer.py only uses it when DINER_B200_EXPERIMENTAL_BACKWARD=1).
+// Backward pass of the render path on fp32 CUDA cores: the training step of BASELINE config 3 (loss + backward through the
+// renderer), checked against the reference's own autograd gradients (tests/test_gpu_parity.py::test_backward_*).
 //
 // What the reference differentiates (src/models/diner.py:257-266 -> nerf_renderer.py:286-365 -> pixelnerf.py:55-145 ->
 // resnetfc.py:129-159): rendered colours w.r.t. the ResnetFC parameters and the latent maps.  The sample depths carry no

@@ -197,6 +197,14 @@ static int check_ready(diner_ctx* c) {
     if (!c) return fail(DINER_E_INVALID, "ctx is NULL");
     if (!c->has_mlp) return fail(DINER_E_STATE, "diner_set_mlp has not been called");
     if (!c->has_scene) return fail(DINER_E_STATE, "diner_set_scene has not been called (PixelNeRF.encode first)");
+    // the MLP and the scene arrive independently through the ABI: every mode sizes its buffers from both, so they must agree
+    // before anything is launched (pixelnerf.py:23-24: d_latent = encoder.latent_size, d_in = poscode + depthcode + 3)
+    if (c->scene.L != c->mlp.d_latent)
+        return fail(DINER_E_INVALID, "the scene has %d latent channels but the MLP expects d_latent=%d", c->scene.L, c->mlp.d_latent);
+    const int d_in = 3 + 6 * c->scene.num_freqs + 3 + 1 + 2 * c->scene.num_freqs;
+    if (d_in != c->mlp.d_in)
+        return fail(DINER_E_INVALID, "the positional code (num_freqs=%d, include_input) gives d_in=%d but lin_in expects %d",
+                    c->scene.num_freqs, d_in, c->mlp.d_in);
     return DINER_OK;
 }
 
@@ -224,11 +232,9 @@ static int run_query(diner_ctx* c, const QueryArgs& q, int mode, cudaStream_t st
     } else if (mode == DINER_MODE_PARITY || mode == DINER_MODE_FAST) {
         if (!c->tc.ready)
             return fail(DINER_E_UNSUPPORTED, "tensor-core path unavailable for this MLP shape: %s", c->tc.why);
-        cudaError_t e = (c->tc.kernel == 2 && (c->scene.L % 64) == 0 && c->scene.L <= 512)
-                            ? tc2_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st)
-                            : tc_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st);
+        cudaError_t e = tc2_query(c->tc, c->scene, c->mlp, q, mode == DINER_MODE_PARITY, c->num_sms, st);
         if (e == cudaErrorNotSupported) return fail(DINER_E_UNSUPPORTED, "tensor-core path: %s", c->tc.why);
-        if (e != cudaSuccess) return fail(DINER_E_CUDA, "tc_query: %s (watchdog code %d)", cudaGetErrorString(e), c->tc.err_flag ? *c->tc.err_flag : -1);
+        if (e != cudaSuccess) return fail(DINER_E_CUDA, "tc2_query: %s (watchdog code %d)", cudaGetErrorString(e), c->tc.err_flag ? *c->tc.err_flag : -1);
     } else {
         return fail(DINER_E_INVALID, "unknown mode %d", mode);
     }
@@ -304,7 +310,7 @@ extern "C" int diner_query(diner_ctx* c, const float* xyz, const float* viewdirs
 }
 
 static int do_composite(diner_ctx* c, const float* rays, const float* z, int SB, int NR, int K, int white,
-                        int mode, float* rgb, float* depth, float* weights, cudaStream_t st) {
+                        int mode, float* rgb, float* depth, float* weights, cudaStream_t st, float* rgbd = nullptr) {
     const long long n_rays = (long long)SB * NR;
     if (n_rays == 0) return DINER_OK;
     CUDA_TRY(c->netbuf.reserve((size_t)n_rays * K * 4 * sizeof(float)));
@@ -314,7 +320,7 @@ static int do_composite(diner_ctx* c, const float* rays, const float* z, int SB,
     int rc = run_query(c, q, mode, st);
     if (rc) return rc;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev2, st));
-    CUDA_TRY(launch_composite(rays, z, q.out, n_rays, K, white, rgb, depth, weights, st));
+    CUDA_TRY(launch_composite(rays, z, q.out, n_rays, K, white, rgb, depth, weights, st, rgbd));
     g_launches++;
     if (c->timing) {
         CUDA_TRY(cudaEventRecord(c->ev3, st));
@@ -360,11 +366,29 @@ extern "C" int diner_render(diner_ctx* c, const float* rays, int SB, int NR, int
     return rc;
 }
 
+extern "C" int diner_render_rgbd(diner_ctx* c, const float* rays, int SB, int NR, int K, int C, int G, int white_bkgd,
+                                 int mode, const diner_noise* noise, float* rgbd, void* stream) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_render_args(c, SB, NR, K, C, G))) return rc;
+    if ((long long)SB * NR == 0) return DINER_OK;
+    if (!rays || !rgbd) return fail(DINER_E_INVALID, "NULL pointer argument");
+    if (((uintptr_t)rgbd & 15) != 0) return fail(DINER_E_INVALID, "rgbd must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(c->zbuf.reserve((size_t)SB * NR * K * sizeof(float)));
+    const long long l0 = g_launches;
+    rc = do_sample(c, rays, SB, NR, K, C, G, noise, c->zbuf.as<float>(), nullptr, st);
+    if (!rc) rc = do_composite(c, rays, c->zbuf.as<float>(), SB, NR, K, white_bkgd, mode, nullptr, nullptr, nullptr, st, rgbd);
+    c->launches += g_launches - l0;
+    return rc;
+}
+
 extern "C" long long diner_mlp_param_count(diner_ctx* c) {
     return (c && c->has_mlp) ? (long long)backward_param_count(c->mlp) : 0;
 }
 
-// EXPERIMENTAL (fp32 CUDA cores; one passing hardware run against the reference gradients so far): gradients of sum(g_rgb . rgb) + sum(g_depth . depth) through
+// Training-step backward (fp32 CUDA cores; checked against the reference's autograd gradients by the GPU tests): gradients of sum(g_rgb . rgb) + sum(g_depth . depth) through
 // composite -> PixelNeRF.forward -> ResnetFC for given sample depths z.
 extern "C" int diner_render_backward(diner_ctx* c, const float* rays, const float* z, int SB, int NR, int K, int white_bkgd,
                                      const float* g_rgb, const float* g_depth, float* grad_params, float* d_latent, void* stream) {
@@ -457,14 +481,11 @@ extern "C" int diner_render_host(diner_ctx* c, const float* rays_host, int SB, i
 
 extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) {
     if (!c || !key) return fail(DINER_E_INVALID, "NULL ctx / key");
-    if (!strcmp(key, "cluster")) {
-        if (value != 1 && value != 2 && value != 4) return fail(DINER_E_INVALID, "cluster must be 1, 2 or 4");
-        c->tc.cluster = (int)value;
-    } else if (!strcmp(key, "kernel")) {
-        if (value != 1 && value != 2) return fail(DINER_E_INVALID, "kernel must be 1 (single-CTA) or 2 (CTA pair)");
-        c->tc.kernel = (int)value;
+    if (!strcmp(key, "tail_kb")) {
+        if (value < 0 || value > 4) return fail(DINER_E_INVALID, "tail_kb must be in [0,4]");
+        c->tc.tail_kb = (int)value;
     } else if (!strcmp(key, "early_split")) {
-        if (value < 1 || value > 7) return fail(DINER_E_INVALID, "early_split must be in [1,7]");
+        if (value < 0 || value > 7) return fail(DINER_E_INVALID, "early_split must be in [0,7]");
         c->tc.early_split = (int)value;
     } else if (!strcmp(key, "rebuild_maps")) {
         c->tc.zmap_valid = false;        // next query rebuilds the hoisted lin_z maps (bench: times the scene-prepare step)

@@ -9,7 +9,7 @@ namespace {
 __global__ void __launch_bounds__(128)
 composite_kernel(const float* __restrict__ rays, const float* __restrict__ z, const float* __restrict__ net,
                  long long n_rays, int K, int white, float* __restrict__ rgb, float* __restrict__ depth,
-                 float* __restrict__ weights) {
+                 float* __restrict__ weights, float4* __restrict__ rgbd) {
     const int lane = threadIdx.x & 31;
     const long long ray = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray >= n_rays) return;
@@ -51,8 +51,12 @@ composite_kernel(const float* __restrict__ rays, const float* __restrict__ z, co
     }
     if (lane == 0) {
         if (white) { ar = (ar + 1.0f) - aw; ag = (ag + 1.0f) - aw; ab = (ab + 1.0f) - aw; }   // (:357-360)
-        rgb[ray * 3 + 0] = ar; rgb[ray * 3 + 1] = ag; rgb[ray * 3 + 2] = ab;
-        depth[ray] = ad;
+        if (rgbd) {                       // packed rgb|depth: the layout the image all-gather sends (diner_render_rgbd)
+            rgbd[ray] = make_float4(ar, ag, ab, ad);
+        } else {
+            rgb[ray * 3 + 0] = ar; rgb[ray * 3 + 1] = ag; rgb[ray * 3 + 2] = ab;
+            depth[ray] = ad;
+        }
     }
 }
 
@@ -60,10 +64,10 @@ composite_kernel(const float* __restrict__ rays, const float* __restrict__ z, co
 
 cudaError_t launch_composite(const float* rays, const float* z, const float* net_out, long long n_rays,
                              int K, int white_bkgd, float* rgb, float* depth, float* weights,
-                             cudaStream_t st) {
+                             cudaStream_t st, float* rgbd) {
     if (n_rays <= 0) return cudaSuccess;
     const long long threads = n_rays * 32;
     composite_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(rays, z, net_out, n_rays, K, white_bkgd,
-                                                                        rgb, depth, weights);
+                                                                        rgb, depth, weights, (float4*)rgbd);
     return cudaGetLastError();
 }

@@ -62,7 +62,7 @@ cudaError_t launch_composite_backward(const float* rays, const float* z, const f
 // --- alpha compositing (composite.cu) -------------------------------------------------------------
 cudaError_t launch_composite(const float* rays, const float* z, const float* net_out, long long n_rays,
                              int K, int white_bkgd, float* rgb, float* depth, float* weights,
-                             cudaStream_t st);
+                             cudaStream_t st, float* rgbd = nullptr);
 
 // --- scene re-layout (scene.cu) ---------------------------------------------------------------------
 cudaError_t launch_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, cudaStream_t st);

@@ -7,7 +7,7 @@
 struct TcState {
     bool ready = false;
     char why[160] = "diner_set_mlp not called";
-    void* wpack = nullptr;        // bf16 hi/lo weight tiles in UMMA K-major SWIZZLE_128B layout
+    void* wpack = nullptr;        // fp16 hi/lo weight tiles (scaled by tc::W_SCALE) in UMMA K-major SWIZZLE_128B layout
     size_t wpack_bytes = 0;
     float* bias = nullptr;        // per-phase cumulative bias vectors
     void* scratch = nullptr;      // combined activations x_c between the pre- and post-combine kernels
@@ -16,13 +16,10 @@ struct TcState {
     int n_pre = 0, n_post = 0;    // ResnetFC blocks before / after the view-combine
     int pairs_pre = 0, pairs_post = 0;   // (hi,lo) weight tile pairs per CTA tile of the PRE / POST kernel
     size_t bias_post_off = 0, bias_pair_off = 0;   // float offsets of the POST rows / the pair kernel's folded PRE rows in `bias`
-    int cluster = 1;              // thread-block cluster size for weight multicast (1, 2 or 4)
     long long sub_batch = 0;      // samples per PRE/POST launch pair (0 = default)
-    int max_grid[3] = {0, 0, 0};
-    int kernel = 2;               // 1 = single-CTA transposed kernel (mlp_tc.cu), 2 = CTA-pair kernel (mlp_tc2.cu)
-    int pairs_post_v1 = 0;        // POST tile pairs the v1 kernel consumes (the pair kernel's zero lin_out tile excluded)
     int* table2 = nullptr;        // pair kernel: per-rank weight tile tables
-    int table2_parity = -1, uses2_zmap = 0, uses2_pre = 0, uses2_post = 0, max_grid2 = 0;
+    int table2_parity = -1, table2_tail = -1, uses2_zmap = 0, uses2_pre = 0, uses2_post = 0, max_grid2 = 0;
+    int tail_kb = 3;              // last K blocks of every full-width GEMM step issued N-tile-outer (see mlp_tc2.cu "accumulator halves")
     float* zmap = nullptr;        // pair kernel: Y_b = lin_z[b](latent) maps, [block][pixel][512] fp32 (hoisted lin_z, see mlp_tc2.cu)
     size_t zmap_bytes = 0;
     bool zmap_valid = false;      // cleared by diner_set_mlp / diner_set_scene; rebuilt lazily by the next query
@@ -31,16 +28,14 @@ struct TcState {
     bool wmap_ok = false;
     CUtensorMap wmap_small;       // same buffer, box = first 16 rows of a tile (2 KiB): lin_out in the pair kernel
     bool wmap_small_ok = false;
-    int early_split = 5;          // pair kernel PRE: worker/helper split of the next tile's early Y_0 gather (tuning)
+    int early_split = 0;          // pair kernel PRE: worker/helper split of the next tile's early Y_0 gather (0 = same as inside a tile)
     int dbg_skip = 0;             // profiling experiments (pair kernel PRE): see tc2::Args::dbg_skip
     bool timing = false;          // per-kernel CUDA-event timing (adds one sync per sub-batch)
     float ms_pre = 0.f, ms_post = 0.f;   // accumulated over the last tc_query call
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // co-resident CTAs for cluster sizes 1, 2, 4 (queried lazily)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st);
-cudaError_t tc_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity,
-                     int num_sms, cudaStream_t st);
 void tc_release(TcState& t);
 cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity,
                       int num_sms, cudaStream_t st);

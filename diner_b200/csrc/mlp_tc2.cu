@@ -29,7 +29,13 @@
 //   * epilogues run in two halves (K blocks 0..3 / 4..7), one operand barrier each, so the next GEMM starts on half 0;
 //   * across tiles: under the last fc_1 the helper warps compute the next tile's taps and lin_in features and everyone gathers
 //     its Y_0 (K blocks 1..7); lin_in of the next tile is handed off right after the view-combine.
+//   * accumulator halves: the first epilogue half reads only N tile 0 of the accumulator (hidden units 0..255 = K blocks 0..3 of
+//     the next layer), so the last `tail` K blocks of every full-width step are issued N-TILE-OUTER -- (kb, n0) for the tail,
+//     commit bar_acc0, then (kb, n1), commit bar_acc -- and that epilogue half runs under the n1 tail of the same GEMM.  It writes
+//     operand K blocks 0..3, which the running GEMM released long ago (tail <= 4); only the second half waits for the full step.
 // mbarrier parity waits are only safe if the waiter cannot be a whole phase late -- see the notes at the helper-warp code.
+// Operands are fp16 hi/lo pairs of W_SCALE-scaled weights and unscaled activations (mlp_tc.cu): every accumulator in TMEM holds
+// W_SCALE * value; the Y maps and the x_c load carry the same factor, the epilogues multiply by W_INV where they add their bias.
 //
 // Reference semantics: src/models/resnetfc.py:61-69,129-159; src/models/pixelnerf.py:91-143; src/models/image_encoder.py:97-146.
 #include "mlp_tc.h"
@@ -56,6 +62,9 @@ using tc::tmem_st32_issue;
 using tc::tmem_st_wait;
 using tc::make_desc;
 using tc::split8;
+using tc::split1;
+using tc::W_SCALE;
+using tc::W_INV;
 using tc::sample_point;
 
 constexpr int ROWS = 64;                    // rows per CTA (128 per pair)
@@ -92,6 +101,7 @@ struct GemmStep {
     short dst_col;     // TMEM column base
     short accumulate;
     short release;     // commit the per-K-block "A operand free" barriers (a gather into A overlaps / follows the step); 2 = lin_in
+    short tail;        // the last `tail` K blocks are issued N-tile-outer (accumulator N tile 0 completes early -> bar_acc0)
 };
 
 struct Args {
@@ -115,6 +125,7 @@ struct Args {
     int* err;
     long long* dbg_ts;          // profiling: clock64 stamps of pair 0 in round 1 ([cta][role][slot])
     int early_worker_kb_hi;     // next-tile Y_0 gather under the last fc_1: K blocks 1..this on the workers, the rest on the helpers
+    int worker_kb_hi;           // Y_b gather inside a tile: K blocks 0..this on the workers (released before the N-outer tail), the rest on the helpers
     int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
 };
 
@@ -139,7 +150,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
         if (++spins > tc::SPIN_LIMIT) { atomicExch(err, code); __threadfence_system(); __trap(); }
     }
 }
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
@@ -148,9 +159,9 @@ __device__ __forceinline__ void umma2_commit_pair(uint32_t bar) {     // arrives
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-// A K-major, B K-major, D f32, bf16 inputs; M = 128 over the pair
+// A K-major, B K-major, D f32 (1 << 4), fp16 inputs (a_format = b_format = 0; bf16 would be 1 << 7 | 1 << 10); M = 128 over the pair
 __host__ __device__ constexpr uint32_t make_idesc2(int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 // byte offset of (row r, 8-wide k chunk kc = k/8) in the K-major SWIZZLE_128B activation operand
 __device__ __forceinline__ uint32_t act_off(int r, int kc) {
@@ -170,17 +181,17 @@ template <bool PARITY> struct Cfg {
 
 // ---- worker building blocks ----------------------------------------------------------------------
 // TMEM region (this warp's N tile: 128 columns) + per-column bias -> relu -> bf16 hi/lo chunks of the A operand
-// 32 accumulator columns of row r (hidden h0..h0+31) + bias -> relu -> four 16-byte K-major chunks (hi / lo)
+// 32 accumulator columns of row r (hidden h0..h0+31): relu(acc * W_INV + bias) -> four 16-byte K-major chunks (hi / lo)
 template <bool PARITY>
 __device__ __forceinline__ void convert32(const uint32_t* v, const float* __restrict__ bias, int h0, int r, uint8_t* Ahi, uint8_t* Alo) {
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
         const float4 b0 = __ldg((const float4*)(bias + h0 + 8 * c8)), b1 = __ldg((const float4*)(bias + h0 + 8 * c8 + 4));
         float x[8];
-        x[0] = fmaxf(__uint_as_float(v[8 * c8 + 0]) + b0.x, 0.0f); x[1] = fmaxf(__uint_as_float(v[8 * c8 + 1]) + b0.y, 0.0f);
-        x[2] = fmaxf(__uint_as_float(v[8 * c8 + 2]) + b0.z, 0.0f); x[3] = fmaxf(__uint_as_float(v[8 * c8 + 3]) + b0.w, 0.0f);
-        x[4] = fmaxf(__uint_as_float(v[8 * c8 + 4]) + b1.x, 0.0f); x[5] = fmaxf(__uint_as_float(v[8 * c8 + 5]) + b1.y, 0.0f);
-        x[6] = fmaxf(__uint_as_float(v[8 * c8 + 6]) + b1.z, 0.0f); x[7] = fmaxf(__uint_as_float(v[8 * c8 + 7]) + b1.w, 0.0f);
+        x[0] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 0]), W_INV, b0.x), 0.0f); x[1] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 1]), W_INV, b0.y), 0.0f);
+        x[2] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 2]), W_INV, b0.z), 0.0f); x[3] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 3]), W_INV, b0.w), 0.0f);
+        x[4] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 4]), W_INV, b1.x), 0.0f); x[5] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 5]), W_INV, b1.y), 0.0f);
+        x[6] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 6]), W_INV, b1.z), 0.0f); x[7] = fmaxf(fmaf(__uint_as_float(v[8 * c8 + 7]), W_INV, b1.w), 0.0f);
         uint4 hi, lo;
         split8(x, hi, lo);
         const uint32_t off = act_off(r, (h0 >> 3) + c8);
@@ -247,10 +258,11 @@ __device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, ui
 #pragma unroll 1
         for (int e = part; e < KBLK; e += PARTS) {
             const float val = e < d_in ? feature_elem(e, s.num_freqs, s.freqs, xc, yc, zc, dxc, dyc, dzc, dd) : 0.0f;
-            const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+            __half hi, lo;
+            split1(val, hi, lo);
             const uint32_t off = act_off(r, e >> 3) + (uint32_t)(e & 7) * 2u;
-            *(__nv_bfloat16*)(Ahi + off) = hi;
-            if (PARITY) *(__nv_bfloat16*)(Alo + off) = __float2bfloat16_rn(val - __bfloat162float(hi));
+            *(__half*)(Ahi + off) = hi;
+            if (PARITY) *(__half*)(Alo + off) = lo;
         }
     }
 }
@@ -262,11 +274,11 @@ __device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, ui
 // bar_afree[0], par1 that of the others (K block 0 has one more release per tile: it also carries the lin_in features).
 // One pass = 4 rows x 64 channels (one K block): lane -> row 4*(p%16) + lane/8, 8 channels (lane%8): 32-byte loads per tap;
 // channels 0..3 of the chunk go to the hi slot, 4..7 to the lo slot (the epilogue thread that owns the row reads them back).
-// Work split: the 8 worker warps take K blocks <= 4 (released early in the running GEMM), the 4 helper warps K blocks 5..7,
-// which are released when that GEMM is about to finish -- the workers run the first epilogue half meanwhile.
+// Work split: the 8 worker warps take K blocks <= WORKER_KB_HI (released in the K-block-outer part of the running GEMM), the 4
+// helper warps the rest, which are released in its N-tile-outer tail -- the workers run the first epilogue half meanwhile.
 __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ ymap, int wwarp, int lane, uint8_t* Ahi,
                                          uint8_t* Alo, const Tap* taps, int kb_lo, int kb_hi, uint32_t bar_afree, uint32_t par0,
-                                         uint32_t par1, int WORKER_KB_HI = 4) {
+                                         uint32_t par1, int WORKER_KB_HI = HID / KBLK - 1) {
     const SceneDev& s = a.s;
     constexpr int PASSES_PER_KB = ROWS / 4;         // 16
     auto issue = [&](int p, float4 (&f)[8], float (&w)[4], uint32_t& off) {
@@ -318,8 +330,8 @@ __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ y
     while (waited < kb_hi) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 46); }
 }
 
-// Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row), written back to TMEM as
-// the residual; relu(x') -> bf16 hi/lo chunks of the fc_0 operand.  The biases that precede this point (b_in / b_fc1[b-1] and
+// Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row; both carry W_SCALE), written
+// back to TMEM as the residual; relu(x') * W_INV -> fp16 hi/lo chunks of the fc_0 operand.  The biases that precede this point (b_in / b_fc1[b-1] and
 // b_z[b]) are folded into Y_b when the maps are built (the four bilinear weights sum to 1), so the residual in TMEM carries them.  Each thread reads and then overwrites
 // only its own (row, k-chunk) slots, so the staging can live in the operand buffers.
 template <bool PARITY>
@@ -336,7 +348,7 @@ __device__ __forceinline__ void add32_convert(uint32_t* v, int h0, int r, uint8_
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[8 * c8 + i] = __float_as_uint(xs[i]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = fmaxf(xs[i], 0.0f);
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(xs[i], 0.0f) * W_INV;
         uint4 hi, lo;
         split8(x, hi, lo);
         *(uint4*)(Ahi + off) = hi;
@@ -377,7 +389,7 @@ __device__ __forceinline__ void load_latent_rows(const Args& a, long long tile, 
         *(uint4*)(Alo + off) = lo;
     }
 }
-// ZMAP: accumulator rows -> Y_b[pixel][512] fp32 (thread = row, 128 contiguous bytes per TMEM load)
+// ZMAP: accumulator rows -> Y_b[pixel][512] fp32, stored WITH the W_SCALE factor of the accumulator (thread = row, 128 contiguous bytes per TMEM load)
 __device__ __forceinline__ void store_y_rows(uint32_t tmem, float* __restrict__ ymap, const float* __restrict__ bias, long long pix, bool write,
                                              int q, int lane, int n2) {
     const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2);
@@ -392,8 +404,8 @@ __device__ __forceinline__ void store_y_rows(uint32_t tmem, float* __restrict__ 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 bv = __ldg(bs + i);
-                dst[i] = make_float4(__uint_as_float(v[4 * i]) + bv.x, __uint_as_float(v[4 * i + 1]) + bv.y, __uint_as_float(v[4 * i + 2]) + bv.z,
-                                     __uint_as_float(v[4 * i + 3]) + bv.w);
+                dst[i] = make_float4(fmaf(bv.x, W_SCALE, __uint_as_float(v[4 * i])), fmaf(bv.y, W_SCALE, __uint_as_float(v[4 * i + 1])),
+                                     fmaf(bv.z, W_SCALE, __uint_as_float(v[4 * i + 2])), fmaf(bv.w, W_SCALE, __uint_as_float(v[4 * i + 3])));
             }
         }
     }
@@ -429,7 +441,7 @@ __device__ __forceinline__ void combine_store(uint32_t* raw, const float* __rest
     constexpr int CNT = 32 / NV;
     if (write) {
 #pragma unroll
-        for (int i = 0; i < CNT; ++i) v[i] = v[i] * (1.0f / (float)NV) + __ldg(cb + h0 + off + i);
+        for (int i = 0; i < CNT; ++i) v[i] = v[i] * (W_INV / (float)NV) + __ldg(cb + h0 + off + i);
         float* dst = dst_sample + h0 + off;
         if constexpr (CNT >= 4) {
 #pragma unroll
@@ -487,8 +499,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     const uint32_t bar_empty = bar_full + 8 * C::NST;              // NST: stage free (pair commit)
     const uint32_t bar_opnd = bar_empty + 8 * C::NST;              // 2: (leader) A operand half h of both CTAs ready
     const uint32_t bar_acc = bar_opnd + 16;                        // accumulators of a GEMM step complete (pair commit)
-    const uint32_t bar_afree = bar_acc + 8;                        // 8: K block kb of the A operand no longer read (pair commit)
-    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + C::OFF_BARS + 8 * (2 * C::NST + 3 + HID / KBLK));
+    const uint32_t bar_acc0 = bar_acc + 8;                         // N tile 0 of the step's accumulator complete (pair commit; before bar_acc)
+    const uint32_t bar_afree = bar_acc0 + 8;                       // 8: K block kb of the A operand no longer read (pair commit)
+    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + C::OFF_BARS + 8 * (2 * C::NST + 4 + HID / KBLK));
 
     if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 90); __trap(); }
     if (threadIdx.x == 0) {
@@ -496,6 +509,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         mbar_init(bar_opnd, NUM_WORKER_WARPS + 1);
         mbar_init(bar_opnd + 8, NUM_WORKER_WARPS + 1);
         mbar_init(bar_acc, 1);
+        mbar_init(bar_acc0, 1);
         for (int i = 0; i < HID / KBLK; ++i) mbar_init(bar_afree + 8 * i, 1);
         fence_barrier_init();
     }
@@ -550,7 +564,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             for (int sidx = 0; sidx < a.n_steps; ++sidx) {
                 const GemmStep gs = a.steps[sidx];
                 const uint32_t idesc = make_idesc2(gs.n_width);
-                for (int kb = 0; kb < gs.nkb; ++kb) {
+                // K blocks [0, kb_split) K-block-outer over both N tiles; the tail [kb_split, nkb) N-tile-outer: N tile 0 of the
+                // accumulator completes `tail` K blocks early (bar_acc0) and its epilogue half overlaps the n1 tail
+                const int kb_split = gs.n_tiles == 2 ? gs.nkb - (gs.tail < gs.nkb ? gs.tail : gs.nkb) : gs.nkb;
+                auto wait_half = [&](int kb) {
                     if ((kb & 3) == 0) {
                         const int h = kb >> 2;
                         mbar_wait(bar_opnd + 8 * h, oph[h] & 1, a.err, 20 + h);
@@ -558,42 +575,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         tc_fence_after();
                         TS(0, 4 * sidx + h);
                     }
-                    for (int n2 = 0; n2 < gs.n_tiles; ++n2) {
-                        const uint32_t d = tmem + (uint32_t)(gs.dst_col + 128 * n2);
-                        {   // W_hi tile: A_hi*W_hi (+ A_lo*W_hi)
-                            const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
-                            mbar_wait(bar_full + 8 * st, ph, a.err, 30);
-                            tc_fence_after();
-                            if (leader) {
-                                const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
-                                const uint64_t ahi = make_desc(smem_base + C::OFF_A_HI + kb * ACT_KB_BYTES, 16, 1024);
-                                const uint64_t alo = make_desc(smem_base + C::OFF_A_LO + kb * ACT_KB_BYTES, 16, 1024);
+                };
+                auto issue_tile = [&](int kb, int n2) {
+                    const uint32_t d = tmem + (uint32_t)(gs.dst_col + 128 * n2);
+                    {   // W_hi tile: A_hi*W_hi (+ A_lo*W_hi)
+                        const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
+                        mbar_wait(bar_full + 8 * st, ph, a.err, 30);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
+                            const uint64_t ahi = make_desc(smem_base + C::OFF_A_HI + kb * ACT_KB_BYTES, 16, 1024);
+                            const uint64_t alo = make_desc(smem_base + C::OFF_A_LO + kb * ACT_KB_BYTES, 16, 1024);
 #pragma unroll
-                                for (int j = 0; j < ((a.dbg_skip & 8) ? 0 : 4); ++j) {
-                                    umma2_bf16(d, ahi + 2 * j, bdesc + 2 * j, idesc, (gs.accumulate | kb | j) ? 1u : 0u);
-                                    if (PARITY) umma2_bf16(d, alo + 2 * j, bdesc + 2 * j, idesc, 1u);
-                                }
-                                umma2_commit_pair(bar_empty + 8 * st);
+                            for (int j = 0; j < ((a.dbg_skip & 8) ? 0 : 4); ++j) {
+                                umma2_f16(d, ahi + 2 * j, bdesc + 2 * j, idesc, (gs.accumulate | kb | j) ? 1u : 0u);
+                                if (PARITY) umma2_f16(d, alo + 2 * j, bdesc + 2 * j, idesc, 1u);
                             }
-                            __syncwarp();
-                            ++use;
+                            umma2_commit_pair(bar_empty + 8 * st);
                         }
-                        if (PARITY) {   // W_lo tile: A_hi*W_lo
-                            const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
-                            mbar_wait(bar_full + 8 * st, ph, a.err, 31);
-                            tc_fence_after();
-                            if (leader) {
-                                const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
-                                const uint64_t ahi = make_desc(smem_base + C::OFF_A_HI + kb * ACT_KB_BYTES, 16, 1024);
-#pragma unroll
-                                for (int j = 0; j < ((a.dbg_skip & 8) ? 0 : 4); ++j) umma2_bf16(d, ahi + 2 * j, bdesc + 2 * j, idesc, 1u);
-                                umma2_commit_pair(bar_empty + 8 * st);
-                            }
-                            __syncwarp();
-                            ++use;
-                        }
+                        __syncwarp();
+                        ++use;
                     }
+                    if (PARITY) {   // W_lo tile: A_hi*W_lo
+                        const uint32_t st = use % C::NST, ph = (use / C::NST) & 1;
+                        mbar_wait(bar_full + 8 * st, ph, a.err, 31);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
+                            const uint64_t ahi = make_desc(smem_base + C::OFF_A_HI + kb * ACT_KB_BYTES, 16, 1024);
+#pragma unroll
+                            for (int j = 0; j < ((a.dbg_skip & 8) ? 0 : 4); ++j) umma2_f16(d, ahi + 2 * j, bdesc + 2 * j, idesc, 1u);
+                            umma2_commit_pair(bar_empty + 8 * st);
+                        }
+                        __syncwarp();
+                        ++use;
+                    }
+                };
+                for (int kb = 0; kb < kb_split; ++kb) {
+                    wait_half(kb);
+                    for (int n2 = 0; n2 < gs.n_tiles; ++n2) issue_tile(kb, n2);
                     if (gs.release && leader) umma2_commit_pair(bar_afree + 8 * kb);
+                    __syncwarp();
+                }
+                for (int n2 = 0; n2 < gs.n_tiles; ++n2) {
+                    for (int kb = kb_split; kb < gs.nkb; ++kb) {
+                        if (n2 == 0) wait_half(kb);
+                        issue_tile(kb, n2);
+                        if (n2 + 1 == gs.n_tiles && gs.release && leader) umma2_commit_pair(bar_afree + 8 * kb);
+                        __syncwarp();
+                    }
+                    if (n2 == 0 && leader) umma2_commit_pair(bar_acc0);      // N tile 0 (or the whole of a single-tile step)
                     __syncwarp();
                 }
                 if (leader) {
@@ -631,6 +662,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 }
                 const long long pix = tile * ROWS + r;
                 for (int b = 0; b < a.n_blocks; ++b) {
+                    mbar_wait(bar_acc0, it & 1, a.err, 49);
                     mbar_wait(bar_acc, it & 1, a.err, 44); ++it;
                     tc_fence_after();
                     if (!helper) {
@@ -663,14 +695,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     if (b == 0 && rd > 0) {      // only K block 0 is left (it held the lin_in features until now)
                         gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tp, 0, 0, bar_afree, ph0 & 1, ph1 & 1); ++ph0;
                     } else {
-                        gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, tp, 0, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1);
+                        gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, tp, 0, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.worker_kb_hi);
                         ++ph0; ++ph1;
                     }
                     TSW();
                     // Helpers never wait on bar_acc in this kernel: they are gated by bar_afree alone.  (A helper that finishes a late
                     // gather could reach a bar_acc wait after the barrier has already completed its NEXT phase -- lin_in of the next
                     // tile is short -- and a parity wait that is one phase late blocks for good.)
-                    if (!helper) { mbar_wait(bar_acc, it & 1, a.err, 40); ++it; }                                       // x complete
+                    if (!helper) mbar_wait(bar_acc0, it & 1, a.err, 40);                                               // x, N tile 0 (hidden 0..255) complete
                     TSW();
                     tc_fence_after();
                     if (helper) {
@@ -685,15 +717,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 0);
                         TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 0..3
                         asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                        mbar_wait(bar_acc, it & 1, a.err, 41); ++it;                                                    // x complete
+                        tc_fence_after();
                         if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 1);
                         TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 4..7
                     }
                     if (!helper) {
-                        mbar_wait(bar_acc, it & 1, a.err, 42); ++it; TSW();
+                        mbar_wait(bar_acc0, it & 1, a.err, 42); TSW();                                                  // net, N tile 0
                         tc_fence_after();
                         const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
                         if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
                         TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 0..3
+                        mbar_wait(bar_acc, it & 1, a.err, 39); ++it;                                                    // net complete
+                        tc_fence_after();
                         if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
                         TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 4..7
                     }
@@ -715,7 +751,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         ++ph0; ++ph1;
                     }
                 }
-                if (!helper) { mbar_wait(bar_acc, it & 1, a.err, 43); ++it; }                                           // fc_1 of the last block complete
+                // last fc_1: a worker warp combines only its own N tile of x, so the n2 == 0 warps start on bar_acc0.  They skip
+                // this phase of bar_acc, which is safe: their next wait on it follows a wait on the NEXT phase of bar_acc0, and the
+                // commits of one issuer complete in order
+                if (!helper) {
+                    mbar_wait(bar_acc0, it & 1, a.err, 43);
+                    if (n2 == 1) mbar_wait(bar_acc, it & 1, a.err, 38);
+                    ++it;
+                }
                 TSW();
                 tc_fence_after();
                 // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
@@ -743,7 +786,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // X read out -> lin_in of the next tile
                 }
             } else {
-                // load x_c: fp32 residual -> TMEM X, relu(x_c) -> A operand
+                // load x_c: W_SCALE * x_c -> TMEM X (the residual the fc_1 steps accumulate onto), relu(x_c) -> A operand
                 long long smp = tile * ROWS + r;
                 if (smp >= a.n_samples) smp = a.n_samples - 1;
 #pragma unroll 1
@@ -754,15 +797,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 f = __ldg(src + i);
-                        v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y);
-                        v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
+                        v[4 * i] = __float_as_uint(f.x * W_SCALE); v[4 * i + 1] = __float_as_uint(f.y * W_SCALE);
+                        v[4 * i + 2] = __float_as_uint(f.z * W_SCALE); v[4 * i + 3] = __float_as_uint(f.w * W_SCALE);
                     }
                     tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
 #pragma unroll
                     for (int c8 = 0; c8 < 4; ++c8) {
                         float x[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[8 * c8 + i]), 0.0f);
+                        for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[8 * c8 + i]), 0.0f) * W_INV;
                         uint4 hi, lo;
                         split8(x, hi, lo);
                         const uint32_t off = act_off(r, (h0 >> 3) + c8);
@@ -775,26 +818,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
                 }
                 for (int b = 0; b < a.n_blocks; ++b) {
-                    mbar_wait(bar_acc, it & 1, a.err, 50); ++it;
-                    tc_fence_after();
                     if (!helper) {
                         const float* b0 = a.bias + (size_t)(a.n_blocks + 1 + b) * HID;
+                        mbar_wait(bar_acc0, it & 1, a.err, 50);                                                         // net, N tile 0
+                        tc_fence_after();
                         epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
                         worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b], K blocks 0..3
+                        mbar_wait(bar_acc, it & 1, a.err, 53); ++it;
+                        tc_fence_after();
                         epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
                         worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                    }
-                    mbar_wait(bar_acc, it & 1, a.err, 51); ++it;
-                    tc_fence_after();
-                    if (!helper) {
                         const float* b1 = a.bias + (size_t)(b + 1) * HID;
+                        mbar_wait(bar_acc0, it & 1, a.err, 51);                                                         // x, N tile 0
+                        tc_fence_after();
                         epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
                         worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> next fc_0 / lin_out
+                        mbar_wait(bar_acc, it & 1, a.err, 54); ++it;
+                        tc_fence_after();
                         epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
                         worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
                     }
                 }
-                mbar_wait(bar_acc, it & 1, a.err, 52); ++it;                     // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
+                if (!helper) {                                                   // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
+                    mbar_wait(bar_acc0, it & 1, a.err, 55);
+                    mbar_wait(bar_acc, it & 1, a.err, 52); ++it;
+                }
                 tc_fence_after();
                 if (!helper && q < 2 && n2 == 0) {
                     uint32_t v[32];
@@ -802,8 +850,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     const long long s_loc = tile * ROWS + r;
                     if (live && s_loc < a.n_samples) {
                         const float4 bo = __ldg((const float4*)(a.bias + (size_t)(2 * a.n_blocks + 1) * HID));
-                        const float x0 = __uint_as_float(v[0]) + bo.x, x1 = __uint_as_float(v[1]) + bo.y;
-                        const float x2 = __uint_as_float(v[2]) + bo.z, x3 = __uint_as_float(v[3]) + bo.w;
+                        const float x0 = fmaf(__uint_as_float(v[0]), W_INV, bo.x), x1 = fmaf(__uint_as_float(v[1]), W_INV, bo.y);
+                        const float x2 = fmaf(__uint_as_float(v[2]), W_INV, bo.z), x3 = fmaf(__uint_as_float(v[3]), W_INV, bo.w);
                         ((float4*)a.out)[a.s_begin + s_loc] = make_float4(1.0f / (1.0f + expf(-x0)), 1.0f / (1.0f + expf(-x1)),
                                                                          1.0f / (1.0f + expf(-x2)), fmaxf(x3, 0.0f));
                     }
@@ -844,15 +892,21 @@ static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cu
     const int kbz = m.d_latent / KBLK, kbh = HID / KBLK;
     std::vector<int> zm[2], pre[2], post[2];
     int layer_pair0 = 0;
+    // ring-use order = the MMA issue order of a step (mlp_pair_kernel): K blocks [0, nkb - tail) K-block-outer, the tail N-tile-outer
     auto layer = [&](std::vector<int>* tab, bool par, int nkb, int n_mt, int n_tiles, int flag = 0) {
+        const int tail = n_tiles == 2 ? (t.tail_kb < nkb ? t.tail_kb : nkb) : 0, kb_split = nkb - tail;
         if (tab)
-            for (int r = 0; r < 2; ++r)
-                for (int kb = 0; kb < nkb; ++kb)
-                    for (int n2 = 0; n2 < n_tiles; ++n2) {
-                        const int pair = layer_pair0 + (2 * n2 + r) * nkb + kb;
-                        tab[r].push_back((2 * pair) | flag);
-                        if (par) tab[r].push_back((2 * pair + 1) | flag);
-                    }
+            for (int r = 0; r < 2; ++r) {
+                auto put = [&](int kb, int n2) {
+                    const int pair = layer_pair0 + (2 * n2 + r) * nkb + kb;
+                    tab[r].push_back((2 * pair) | flag);
+                    if (par) tab[r].push_back((2 * pair + 1) | flag);
+                };
+                for (int kb = 0; kb < kb_split; ++kb)
+                    for (int n2 = 0; n2 < n_tiles; ++n2) put(kb, n2);
+                for (int n2 = 0; n2 < n_tiles; ++n2)
+                    for (int kb = kb_split; kb < nkb; ++kb) put(kb, n2);
+            }
         layer_pair0 += n_mt * nkb;
     };
     layer(pre, parity, 1, 4, 2);                                     // lin_in
@@ -873,6 +927,7 @@ static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cu
     TCK(cudaMemcpyAsync(t.table2, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     TCK(cudaStreamSynchronize(st));                                  // `flat` is a stack-lifetime host buffer
     t.table2_parity = (int)parity;
+    t.table2_tail = t.tail_kb;
     return cudaSuccess;
 }
 
@@ -910,7 +965,7 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
     z.uses_per_tile = t.uses2_zmap;
     z.bias = t.bias; z.bias2 = t.bias + t.bias_pair_off;
     z.n_blocks = t.n_pre;
-    for (int b = 0; b < t.n_pre; ++b) z.steps[b] = GemmStep{(short)(m.d_latent / KBLK), 2, 256, COL_X, 0, 0};
+    for (int b = 0; b < t.n_pre; ++b) z.steps[b] = GemmStep{(short)(m.d_latent / KBLK), 2, 256, COL_X, 0, 0, (short)t.tail_kb};
     z.n_steps = t.n_pre;
     z.zmap = t.zmap; z.zmap_stride = n_pix * HID; z.n_pix = n_pix;
     z.n_tiles = (n_pix + ROWS - 1) / ROWS;
@@ -940,7 +995,10 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     const long long total = (long long)q.SB * q.n_per_sb;
     const int kbh = HID / KBLK;
 
-    if (!t.table2 || t.table2_parity != (int)parity) TCK(tc2_build_tables(t, m, parity, st));
+    if (!t.table2 || t.table2_parity != (int)parity || t.table2_tail != t.tail_kb) {
+        TCK(tc2_build_tables(t, m, parity, st));
+        t.zmap_valid = false;            // (the ZMAP launch reads the same tables; nothing else depends on them)
+    }
     int grid_cap = 2;
     TCK(tc2_grid_cap(t, num_sms, &grid_cap));
     if (t.timing && !t.ev[0]) for (int i = 0; i < 4; ++i) TCK(cudaEventCreate(&t.ev[i]));
@@ -965,18 +1023,19 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.n_blocks = t.n_pre; post.n_blocks = t.n_post;
     pre.zmap = t.zmap; pre.zmap_stride = (long long)s.SB * s.NV * s.Hl * s.Wl * HID;
     int n = 0;
-    pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0, 2};                                // lin_in; followed by the gather of Y_0 (K block 0)
+    const short tl = (short)t.tail_kb;
+    pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0, 2, tl};                            // lin_in; followed by the gather of Y_0 (K block 0)
     for (int b = 0; b < t.n_pre; ++b) {
-        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0};                 // fc_0[b]
-        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 1};                   // fc_1[b]; overlapped by the gather of Y_{b+1} / the next tile's Y_0
+        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0, tl};             // fc_0[b]
+        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 1, tl};               // fc_1[b]; overlapped by the gather of Y_{b+1} / the next tile's Y_0
     }
     pre.n_steps = n;
     n = 0;
     for (int b = 0; b < t.n_post; ++b) {
-        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0};
-        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 0};
+        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0, tl};
+        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 0, tl};
     }
-    post.steps[n++] = GemmStep{(short)kbh, 1, 32, COL_NET, 0, 0};
+    post.steps[n++] = GemmStep{(short)kbh, 1, 32, COL_NET, 0, 0, 0};
     post.n_steps = n;
     pre.NV = post.NV = NV;
     pre.spv = post.spv = ROWS / NV;
@@ -985,7 +1044,9 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.err = post.err = t.err_flag;
     pre.n_total = post.n_total = total;
     pre.dbg_skip = t.dbg_skip; post.dbg_skip = 0;
-    pre.early_worker_kb_hi = t.early_split;
+    // workers gather the K blocks that are released in the K-block-outer part of the running GEMM, helpers those of its tail
+    pre.worker_kb_hi = t.tail_kb > 0 ? HID / KBLK - 1 - t.tail_kb : 4;
+    pre.early_worker_kb_hi = t.early_split > 0 ? t.early_split : pre.worker_kb_hi;
     static long long* dbg_ts = nullptr;      // device memory (managed memory would page-fault inside the kernel and distort the timeline)
     if ((t.dbg_skip & 512) && !dbg_ts) TCK(cudaMalloc((void**)&dbg_ts, 8 * 64 * sizeof(long long)));
     if (t.dbg_skip & 512) TCK(cudaMemsetAsync(dbg_ts, 0, 8 * 64 * sizeof(long long), st));

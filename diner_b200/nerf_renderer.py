@@ -19,9 +19,6 @@ except Exception:                       # same attribute-access contract without
             self[k] = v
 
 
-EXPERIMENTAL_BACKWARD = "DINER_B200_EXPERIMENTAL_BACKWARD"   # =1 enables the (not yet hardware-validated) fp32 backward
-
-
 def mlp_param_order(mlp):
     """Names of the ResnetFC parameters in libdiner_b200's canonical order (the argument order of diner_set_mlp)."""
     names = ["lin_in.weight", "lin_in.bias", "lin_out.weight", "lin_out.bias"]
@@ -34,7 +31,9 @@ def mlp_param_order(mlp):
 
 class _RenderWithGrad(torch.autograd.Function):
     """Training-step path (src/models/diner.py:257-266): forward through the fused kernels, backward through
-    diner_render_backward (EXPERIMENTAL, fp32 CUDA cores).  Gradients reach the ResnetFC parameters and encoder.latent."""
+    diner_render_backward (fp32 CUDA cores; validated against the reference's autograd gradients in tests/test_gpu_parity.py).
+    Gradients reach the ResnetFC parameters and encoder.latent; the sampler is @torch.no_grad in the reference too
+    (nerf_renderer.py:65)."""
 
     @staticmethod
     def forward(ctx, renderer, model, rays, latent, *params):
@@ -104,9 +103,8 @@ class NeRFRendererDGS(torch.nn.Module):
     def forward(self, model, rays, want_weights=False):
         """rays (SB,B,8) [origin3, dir3, near, far] -> DotMap(fine=DotMap(rgb (SB,B,3), depth (SB,B)[, weights]))."""
         assert len(rays.shape) == 3
-        import os
-        if (torch.is_grad_enabled() and os.environ.get(EXPERIMENTAL_BACKWARD) == "1" and not want_weights and
-                any(p.requires_grad for p in model.mlp_fine.parameters())):
+        if (torch.is_grad_enabled() and not want_weights and
+                (any(p.requires_grad for p in model.mlp_fine.parameters()) or model.encoder.latent.requires_grad)):
             named = dict(model.mlp_fine.named_parameters())
             params = [named[k] for k in mlp_param_order(model.mlp_fine)]
             rgb, depth = _RenderWithGrad.apply(self, model, rays.float().contiguous(), model.encoder.latent, *params)
@@ -116,6 +114,14 @@ class NeRFRendererDGS(torch.nn.Module):
             rays.float().contiguous(), int(self.n_samples), int(self.n_depth_candidates), int(self.n_gaussian),
             self.white_bkgd, model.mode_id(), self._noise_for_call(), want_weights=want_weights)
         return DotMap(fine=self._format_outputs(w, rgb, depth, want_weights))
+
+    @torch.no_grad()
+    def render_packed(self, model, rays, out=None):
+        """forward() with the outputs packed as (SB,B,4) = [r,g,b,depth] (optionally written into `out`): what the ray-sharded
+        multi-GPU render all-gathers (diner_b200/multi_gpu.py)."""
+        assert len(rays.shape) == 3
+        return model.context().render_rgbd(rays.float().contiguous(), int(self.n_samples), int(self.n_depth_candidates),
+                                           int(self.n_gaussian), self.white_bkgd, model.mode_id(), self._noise_for_call(), out=out)
 
     @torch.no_grad()
     def render_image(self, model, target_extrinsics, target_intrinsics, H, W, z_near, z_far):

@@ -26,7 +26,7 @@ def predict_imgs_from_batch(nerf, renderer, batch, znear, zfar, return_depth=Fal
 def calc_losses(nerf, renderer, batch, znear, zfar, ray_batch_size, generator=None, encode=True):
     """Training-step loss of the reference (src/models/diner.py:217-290) for w_vgg = w_antibias = 0: random pixels of the target
     view(s) (`torch.randint`, :232), their rays through NeRFRendererDGS.forward, MSE against the target colours (:259-266).
-    Gradients need the experimental backward (DINER_B200_EXPERIMENTAL_BACKWARD=1, see nerf_renderer.py); the perceptual /
+    Gradients flow through diner_render_backward (the autograd Function in nerf_renderer.py); the perceptual /
     anti-bias terms of the reference operate on the rendered patch afterwards and stay in PyTorch."""
     SB, _, H, W = batch["target_rgb"].shape
     if encode:

@@ -190,3 +190,41 @@ def gen_rays(extrinsics, intrinsics, W, H, z_near, z_far):
     nr = z_near.view(B, 1, 1, 1).expand(-1, H, W, -1)
     fr = z_far.view(B, 1, 1, 1).expand(-1, H, W, -1)
     return torch.cat((org, d_w, nr, fr), -1)
+
+
+# ----------------------------------------------------------------------------------------------
+# product modules on a device from synthetic case inputs (bench.py, __graft_entry__.smoke(), tests)
+# ----------------------------------------------------------------------------------------------
+def product_model(batch, latent, mlp, device, mode="fp32"):
+    """PixelNeRF (reference constructor arguments of configs/train_dtu.yaml:32-50) with the given ResnetFC weights, the
+    synthetic scene installed as PixelNeRF.encode would leave it (pixelnerf.py:35-53) minus the ResNet trunk: the latent
+    maps are supplied.  `mode` = 'fp32' | 'parity' | 'fast' (diner_b200.pixelnerf)."""
+    from .pixelnerf import PixelNeRF
+    from .scene_ops import depth2normal
+    model = PixelNeRF(
+        poscode_conf=dict(kwargs=dict(num_freqs=6, freq_factor=6.28, include_input=True)),
+        encoder_conf=dict(module="src.models.image_encoder.SpatialEncoder",
+                          kwargs=dict(image_padding=64, padding_pe=4, pretrained=False)),
+        mlp_fine_conf=dict(module="src.models.resnetfc.ResnetFC",
+                           kwargs=dict(n_blocks=5, d_hidden=512, combine_layer=3, combine_type="average")))
+    model.mlp_fine.load_state_dict(mlp)
+    model = model.to(device).eval()
+    SB, NV = batch["src_depths"].shape[:2]
+    H, W = batch["src_depths"].shape[-2:]
+    K = batch["src_intrinsics"].to(device)
+    dep = batch["src_depths"].to(device)
+    nrm = depth2normal(dep.flatten(end_dim=1), K.flatten(end_dim=1)).reshape(SB, NV, 3, H, W)
+    model.encoder.set_scene(latent.to(device), dep, batch["src_depth_stds"].to(device), nrm)
+    model.set_cameras(batch["src_extrinsics"].to(device), K, W, H)
+    model.mode = mode
+    return model
+
+
+def renderer_for(cfg, noise=None, device="cuda"):
+    """NeRFRendererDGS for a case dict (K, C, G, white), optionally with dense injected noise."""
+    from .nerf_renderer import NeRFRendererDGS
+    r = NeRFRendererDGS(n_samples=cfg["K"], n_depth_candidates=cfg["C"], n_gaussian=cfg["G"],
+                        white_bkgd=cfg["white"])
+    if noise is not None:
+        r.noise = {k: (v.to(device).contiguous() if torch.is_tensor(v) else v) for k, v in noise.items()}
+    return r

@@ -33,8 +33,8 @@ extern "C" {
 
 /* Arithmetic mode of the per-sample MLP (ResnetFC). */
 #define DINER_MODE_FP32 0     /* CUDA-core fp32 FMA: reference arithmetic, slow; parity anchor            */
-#define DINER_MODE_PARITY 1   /* tcgen05 bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accum): <=1e-4 vs fp32 */
-#define DINER_MODE_FAST 2     /* tcgen05 single-pass bf16, fp32 accum: PSNR-level agreement only          */
+#define DINER_MODE_PARITY 1   /* tcgen05 fp16x3 split (hi*hi + lo*hi + hi*lo, fp32 accum): ~1e-6 vs fp32  */
+#define DINER_MODE_FAST 2     /* tcgen05 single-pass fp16, fp32 accum: PSNR-level agreement only          */
 
 typedef struct diner_ctx diner_ctx;
 
@@ -89,6 +89,12 @@ int diner_render(diner_ctx* ctx, const float* rays, int SB, int NR, int K, int C
                  int mode, const diner_noise* noise, float* rgb, float* depth, float* weights, float* z,
                  void* stream);
 
+/* Same render with the outputs packed as rgbd (SB,NR,4) = [r,g,b,depth] per ray (16-byte aligned): the layout the multi-GPU
+ * image all-gather sends (diner_b200/multi_gpu.py; SURVEY 8(e): one ncclAllGather of rgb|depth per image), written in place into
+ * the rank's slice of the gather buffer so that no pack / unpack pass runs between the compositing kernel and the collective. */
+int diner_render_rgbd(diner_ctx* ctx, const float* rays, int SB, int NR, int K, int C, int G, int white_bkgd, int mode,
+                      const diner_noise* noise, float* rgbd, void* stream);
+
 /* Whole-image entry: ray generation (gen_rays, src/util/cam_geometry.py:5-48) + the ray_batch_size chunk loop and torch.cat of
  * DINER.predict_imgs_from_batch (src/models/diner.py:79-92) in one call.  target_extrinsics (SB,4,4) world->cam, target_intrinsics
  * (SB,3,3), device fp32; rays are generated on the device for every pixel centre of the H x W target view (row-major) and never
@@ -105,11 +111,10 @@ int diner_gen_rays(diner_ctx* ctx, const float* target_extrinsics, const float* 
 int diner_depth2normal(diner_ctx* ctx, const float* depths, const float* intrinsics, int N, int H, int W, float* normals,
                        void* stream);
 
-/* EXPERIMENTAL -- backward of the render path for the training step (src/models/diner.py:257-266: MSE on the rendered colours,
- * autograd through NeRFRendererDGS.composite / PixelNeRF.forward / ResnetFC; the sampler is @torch.no_grad).  fp32 CUDA cores,
- * correctness anchor for a tcgen05 version; one passing hardware run against the reference's gradients so far
- * (tests/test_gpu_parity.py::test_backward_matches_reference_gradients), so the Python modules only use it when
- * DINER_B200_EXPERIMENTAL_BACKWARD=1.  Given the sample depths z (SB,NR,K) of the forward call and the upstream gradients
+/* Backward of the render path for the training step (src/models/diner.py:257-266: MSE on the rendered colours, autograd
+ * through NeRFRendererDGS.composite / PixelNeRF.forward / ResnetFC; the sampler is @torch.no_grad).  fp32 CUDA cores (the
+ * correctness anchor for a tcgen05 version), checked against the reference's own autograd gradients in
+ * tests/test_gpu_parity.py::test_backward_*.  Given the sample depths z (SB,NR,K) of the forward call and the upstream gradients
  * g_rgb (SB,NR,3), g_depth (SB,NR) or NULL, ACCUMULATES
  *   grad_params: diner_mlp_param_count() floats in the order of diner_set_mlp's arguments (lin_in w,b; lin_out w,b; per block
  *                fc_0 w,b, fc_1 w,b; per lin_z block w,b)
@@ -136,9 +141,10 @@ int diner_query(diner_ctx* ctx, const float* xyz, const float* viewdirs, int SB,
 int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, int NR, int K, int white_bkgd,
                     int mode, float* rgb, float* depth, float* weights, void* stream);
 
-/* Tuning knobs of the tcgen05 path (not part of the reference API): key = "cluster" (thread-block cluster size for
- * weight multicast of kernel 1: 1, 2 or 4), "kernel" (1 = single-CTA tcgen05 kernel, 2 = CTA-pair cta_group::2 kernel, default)
- * "sub_batch" (samples per PRE/POST launch pair) or "rebuild_maps" (forces the next query to rebuild the hoisted lin_z maps). */
+/* Tuning knobs of the tcgen05 path (not part of the reference API): key = "tail_kb" (0..4: K blocks of every GEMM step issued
+ * N-tile-outer so that the first epilogue half overlaps the step's tail), "early_split" (worker/helper split of the next tile's
+ * early gather), "sub_batch" (samples per PRE/POST launch pair) or "rebuild_maps" (forces the next query to rebuild the hoisted
+ * lin_z maps). */
 int diner_set_option(diner_ctx* ctx, const char* key, long long value);
 
 /* cudaDeviceSynchronize + decoded tcgen05 watchdog code on failure (debugging aid). */

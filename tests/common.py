@@ -1,34 +1,22 @@
-"""Shared builders for the tests: product model on a device from the synthetic case inputs."""
+"""Shared builders for the tests.  The product-side builders live in the package (diner_b200.synthetic); the oracle-side
+helper here moves an oracle Scene to a device so that the reference algorithm can be run as eager PyTorch on cuda."""
+import copy
+
 import torch
 
-from diner_b200.nerf_renderer import NeRFRendererDGS
-from diner_b200.pixelnerf import PixelNeRF
-from diner_b200.scene_ops import depth2normal
+from diner_b200.synthetic import product_model, renderer_for  # noqa: F401  (re-exported for the tests)
 
 
-def product_model(batch, latent, mlp, device, mode="fp32"):
-    model = PixelNeRF(
-        poscode_conf=dict(kwargs=dict(num_freqs=6, freq_factor=6.28, include_input=True)),
-        encoder_conf=dict(module="src.models.image_encoder.SpatialEncoder",
-                          kwargs=dict(image_padding=64, padding_pe=4, pretrained=False)),
-        mlp_fine_conf=dict(module="src.models.resnetfc.ResnetFC",
-                           kwargs=dict(n_blocks=5, d_hidden=512, combine_layer=3, combine_type="average")))
-    model.mlp_fine.load_state_dict(mlp)
-    model = model.to(device).eval()
-    SB, NV = batch["src_depths"].shape[:2]
-    H, W = batch["src_depths"].shape[-2:]
-    K = batch["src_intrinsics"].to(device)
-    dep = batch["src_depths"].to(device)
-    nrm = depth2normal(dep.flatten(end_dim=1), K.flatten(end_dim=1)).reshape(SB, NV, 3, H, W)
-    model.encoder.set_scene(latent.to(device), dep, batch["src_depth_stds"].to(device), nrm)
-    model.set_cameras(batch["src_extrinsics"].to(device), K, W, H)
-    model.mode = mode
-    return model
+def oracle_scene_on(scene, device):
+    """Copy of an oracle Scene (built on the host: depth2normal uses host index tensors) with every tensor on `device`."""
+    s = copy.copy(scene)
+    for f in ("poses", "focal", "c", "image_shape", "latent", "depths", "depths_std", "normals"):
+        setattr(s, f, getattr(scene, f).to(device))
+    s.mlp = {k: v.to(device) for k, v in scene.mlp.items()}
+    return s
 
 
-def renderer_for(cfg, noise=None, device="cuda"):
-    r = NeRFRendererDGS(n_samples=cfg["K"], n_depth_candidates=cfg["C"], n_gaussian=cfg["G"],
-                        white_bkgd=cfg["white"])
-    if noise is not None:
-        r.noise = {k: v.to(device).contiguous() for k, v in noise.items()}
-    return r
+def ray_err(rgb, depth, rgb_ref, depth_ref):
+    """Per-ray max |err| over rgb and depth; NaN / inf anywhere counts as +inf (never as 'good')."""
+    e = torch.maximum((rgb - rgb_ref).abs().max(dim=-1).values, (depth - depth_ref).abs())
+    return torch.where(torch.isfinite(e), e, torch.full_like(e, float("inf")))

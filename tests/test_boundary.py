@@ -80,8 +80,10 @@ def test_no_cpu_fallback():
             NeRFRendererDGS()(m, rays)
         with pytest.raises(RuntimeError, match="CUDA"):
             m(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        NeRFRendererDGS()(m, rays)        # grad enabled (training step): same loud failure, no autograd-through-PyTorch fallback
     with pytest.raises(NotImplementedError):
-        NeRFRendererDGS()(m, rays)        # grad enabled -> backward not built, must say so
+        m(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))     # PixelNeRF.forward on its own has no backward
 
 
 def test_scene_ops_match_oracle():

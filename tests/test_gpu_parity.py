@@ -1,11 +1,17 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the committed reference
-goldens (tests/golden, produced by the unmodified reference) and against the CPU oracle.
+goldens (tests/golden, produced by the unmodified reference on torch-CPU), against the CPU oracle,
+and against the same oracle executed as eager PyTorch ON THE GPU (the reference's own deployment
+target: src/models runs on cuda in python_scripts/train.py / create_prediction_folder.py).
 
-Tolerances: north_star asks for 1e-4 abs on rgb / depth.  Stage-wise comparisons (same sample
-depths in) must meet it on every ray.  End-to-end comparisons additionally go through the
-sampler's discontinuous decisions (nearest-pixel lookups, top-K membership); there a ray may
-legitimately differ if a 1-ulp difference flips such a decision, so the test bounds the *fraction*
-of such rays (<= 1%) and requires 1e-4 on all the others.
+Tolerances: north_star asks for 1e-4 abs on rgb / depth (TOL).  The tcgen05 parity mode (fp16 hi/lo
+split operands, fp32 accumulation) is held to PAR_TOL = 2e-5 wherever the sample depths are given.
+Stage-wise comparisons (same sample depths in) must meet the bar on EVERY ray, NaN counting as a
+failure.  End-to-end comparisons additionally go through the sampler's discontinuous decisions
+(nearest-pixel lookups, "likelihood != 0" membership of the shortlist).  Those decisions hinge on the
+last ulp of erf(), on which torch-CPU (Sleef) and torch-CUDA (CUDA libm erff) disagree -- i.e. the
+reference disagrees with itself across its two backends on a few ill-conditioned rays.  The CUDA path
+must therefore (a) match the reference-on-cuda on ALL rays, and (b) differ from the CPU goldens only
+on rays where the reference-on-cuda differs from them as well.
 """
 import os
 
@@ -14,11 +20,19 @@ import torch
 
 from oracle import diner_oracle as O
 from oracle import make_golden as MG
-from tests.common import product_model, renderer_for
+from tests.common import product_model, renderer_for, oracle_scene_on, ray_err
 
 pytestmark = pytest.mark.gpu
 CASES = list(MG.CASES)
-TOL = 1e-4
+ALL_CASES = list(MG.CASES) + list(MG.EXTRA_CASES)
+TOL = 1e-4          # north_star bar
+PAR_TOL = 2e-5      # what the fp16x3 parity mode is held to on given sample depths
+Z_TOL = 1e-5        # sample depths: a different shortlist decision moves a sample by >= one candidate step (>= 1e-3)
+
+
+def _bad(e, tol):
+    """Rays beyond tol; non-finite errors are bad (NaN compares False against everything)."""
+    return ~(e <= tol)
 
 
 def _load(golden_dir, name):
@@ -28,33 +42,38 @@ def _load(golden_dir, name):
     return g, cfg, batch, latent, mlp, rays, noise
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_sampler_matches_reference(golden_dir, name):
+    """sample_depthguided + fill_up_uniform_samples (nerf_renderer.py:65-190,367-397) with the reference's noise injected:
+    (a) against the reference algorithm run on cuda: every ray; (b) against the CPU goldens: every ray on which the
+    reference's two backends agree with each other."""
     g, cfg, batch, latent, mlp, rays, noise = _load(golden_dir, name)
     model = product_model(batch, latent, mlp, "cuda")
     nz = {k: v.cuda().contiguous() for k, v in noise.items()}
     z, zd = model.context().sample(rays.cuda(), cfg["K"], cfg["C"], cfg["G"], nz, want_dgs=True)
-    ref_dgs = g["z_depthguided"].sort(dim=-1).values
-    ray_ok = ((zd.cpu() - ref_dgs).abs().max(dim=-1).values <= 1e-5)
-    fill_ok = ((z.cpu() - g["z_filled"]).abs().max(dim=-1).values <= 1e-5)
-    # Rays whose shortlist reaches into candidates with likelihood at the erf-saturation noise floor
-    # (0.5*|erf(a)-erf(b)| of a few 1e-8): whether such a candidate counts as "non-zero" (nerf_renderer.py:176)
-    # depends on the last ulp of erf, on which torch-CPU (Sleef) and CUDA erff disagree -- the reference
-    # itself is not self-consistent there across its own backends.  Everything else must match.
-    scene = O.make_scene_state(batch, latent, mlp)
-    lik = O.candidate_likelihood(scene, rays, O.sample_coarse(rays, cfg["C"], noise["u_coarse"]))
-    nt = cfg["K"] - cfg["G"]
-    kth = lik.sort(dim=-1, descending=True).values[..., nt - 1] if nt > 0 else torch.ones(lik.shape[:2])
-    well = (kth > 1e-5) | (lik.max(dim=-1).values == 0)
-    print("%s: rays exact %.4f (filled %.4f); well-conditioned rays %.3f, exact among them %.4f" % (
-        name, ray_ok.float().mean(), fill_ok.float().mean(), well.float().mean(), ray_ok[well].float().mean()))
-    assert bool(ray_ok[well].all()) and bool(fill_ok[well].all())
-    assert ray_ok.float().mean() >= 0.95 and fill_ok.float().mean() >= 0.95
+    assert bool(torch.isfinite(z).all()) and bool(torch.isfinite(zd).all())
+    # (a) reference algorithm as eager PyTorch on this GPU
+    sc = oracle_scene_on(O.make_scene_state(batch, latent, mlp), "cuda")
+    with torch.no_grad():
+        zc_dgs = O.sample_depthguided(sc, rays.cuda(), cfg["K"], cfg["C"], cfg["G"], nz["u_coarse"], nz["g_noise"])
+        zc = O.fill_up_uniform(zc_dgs, rays.cuda(), nz["u_fill"])
+    dev_dgs = (zd - zc_dgs.sort(dim=-1).values).abs().max(dim=-1).values.cpu()
+    dev_fill = (z - zc).abs().max(dim=-1).values.cpu()
+    # (b) CPU goldens of the unmodified reference
+    cpu_dgs = (zd.cpu() - g["z_depthguided"].sort(dim=-1).values).abs().max(dim=-1).values
+    cpu_fill = (z.cpu() - g["z_filled"]).abs().max(dim=-1).values
+    ref_split = _bad((zc.cpu() - g["z_filled"]).abs().max(dim=-1).values, Z_TOL)      # reference(cuda) != reference(cpu)
+    print("%s: vs reference-on-cuda: rays exact %.4f (filled %.4f) | vs CPU golden: %.4f (filled %.4f) | rays where the "
+          "reference's own backends differ: %.4f" % (name, (dev_dgs <= Z_TOL).float().mean(), (dev_fill <= Z_TOL).float().mean(),
+                                                     (cpu_dgs <= Z_TOL).float().mean(), (cpu_fill <= Z_TOL).float().mean(),
+                                                     ref_split.float().mean()))
+    assert not bool(_bad(dev_dgs, Z_TOL).any()) and not bool(_bad(dev_fill, Z_TOL).any()), "differs from the reference on cuda"
+    assert not bool((_bad(cpu_fill, Z_TOL) & ~ref_split).any()), "differs from the CPU golden on a ray where the reference agrees with itself"
     assert bool((z[..., 1:] >= z[..., :-1]).all()), "samples must be sorted ascending"
 
 
-@pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("parity", 1e-4)])
+@pytest.mark.parametrize("name", ALL_CASES)
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("parity", PAR_TOL)])
 def test_query_stagewise(golden_dir, name, mode, tol):
     """PixelNeRF.forward on the reference's own sample positions (no RNG, no sampler decisions)."""
     g, cfg, batch, latent, mlp, rays, noise = _load(golden_dir, name)
@@ -64,16 +83,15 @@ def test_query_stagewise(golden_dir, name, mode, tol):
     vd = rays[..., None, 3:6].expand(-1, -1, cfg["K"], -1).reshape(cfg["SB"], -1, 3)
     with torch.no_grad():
         out = model(pts.cuda(), vd.cuda().contiguous()).cpu()
-    ref = g["net_out"]
+    ref = g["net_out"].reshape(out.shape)
+    assert bool(torch.isfinite(out).all())
     err_rgb = (out[..., :3] - ref[..., :3]).abs().max()
     rel_sig = ((out[..., 3] - ref[..., 3]).abs() / (1.0 + ref[..., 3].abs())).max()
     print("%s/%s: max|d rgb| %.3g  max rel|d sigma| %.3g" % (name, mode, err_rgb, rel_sig))
-    # sigma only enters the image through alpha = 1 - exp(-delta * sigma) with delta ~ 1e-2: its relative tolerance is
-    # 2x looser than the 1e-4 absolute bar on colours; the rendered rgb / depth checks below are the north_star bar
-    assert err_rgb <= tol and rel_sig <= 2 * tol
+    assert err_rgb <= tol and rel_sig <= tol
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 @pytest.mark.parametrize("mode", ["fp32", "parity"])
 def test_composite_stagewise(golden_dir, name, mode):
     g, cfg, batch, latent, mlp, rays, noise = _load(golden_dir, name)
@@ -85,24 +103,36 @@ def test_composite_stagewise(golden_dir, name, mode):
     e_d = (depth.cpu() - g["depth"]).abs().max()
     e_w = (w.cpu() - g["weights"]).abs().max()
     print("%s/%s: max|d rgb| %.3g |d depth| %.3g |d w| %.3g" % (name, mode, e_rgb, e_d, e_w))
-    assert e_rgb <= TOL and e_d <= TOL and e_w <= TOL
+    assert bool(torch.isfinite(rgb).all()) and bool(torch.isfinite(depth).all()) and bool(torch.isfinite(w).all())
+    assert e_rgb <= PAR_TOL and e_d <= PAR_TOL and e_w <= PAR_TOL
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 @pytest.mark.parametrize("mode", ["fp32", "parity"])
 def test_render_end_to_end(golden_dir, name, mode):
-    """NeRFRendererDGS.forward with the reference's noise injected vs the reference's output."""
+    """NeRFRendererDGS.forward with the reference's noise injected: (a) vs the reference algorithm on cuda: 1e-4 on EVERY ray
+    (rgb, depth and the compositing weights); (b) vs the CPU goldens of the unmodified reference: 1e-4 on every ray on which
+    the reference-on-cuda agrees with the reference-on-cpu."""
     g, cfg, batch, latent, mlp, rays, noise = _load(golden_dir, name)
     model = product_model(batch, latent, mlp, "cuda", mode)
     rend = renderer_for(cfg, noise)
     with torch.no_grad():
         out = rend(model, rays.cuda(), want_weights=True)
-    e = torch.maximum((out.fine.rgb.cpu() - g["rgb"]).abs().max(dim=-1).values,
-                      (out.fine.depth.cpu() - g["depth"]).abs())
-    frac_bad = (e > TOL).float().mean()
-    print("%s/%s: rays beyond 1e-4: %.4f  (median err %.3g, max %.3g)" % (name, mode, frac_bad, e.median(), e.max()))
-    assert frac_bad <= 0.03     # see test_sampler_matches_reference: erf-noise-floor rays
     assert out.fine.weights.shape == g["weights"].shape
+    sc = oracle_scene_on(O.make_scene_state(batch, latent, mlp), "cuda")
+    nz = rend.noise
+    with torch.no_grad():
+        rgb_c, depth_c, w_c = O.render(sc, rays.cuda(), cfg["K"], cfg["C"], cfg["G"], cfg["white"], nz["u_coarse"], nz["g_noise"], nz["u_fill"])
+    e_dev = ray_err(out.fine.rgb, out.fine.depth, rgb_c, depth_c).cpu()
+    e_w = (out.fine.weights - w_c).abs().max(dim=-1).values.cpu()
+    e_cpu = ray_err(out.fine.rgb.cpu(), out.fine.depth.cpu(), g["rgb"], g["depth"])
+    ref_split = _bad(ray_err(rgb_c.cpu(), depth_c.cpu(), g["rgb"], g["depth"]), TOL)
+    print("%s/%s: vs reference-on-cuda max |err| %.3g (weights %.3g) | vs CPU golden: rays beyond 1e-4 %.4f, of which the "
+          "reference's own backends differ on %.4f; max elsewhere %.3g" % (
+              name, mode, e_dev.max(), e_w.max(), _bad(e_cpu, TOL).float().mean(), (_bad(e_cpu, TOL) & ref_split).float().mean(),
+              e_cpu[~ref_split].max() if bool((~ref_split).any()) else 0.0))
+    assert not bool(_bad(e_dev, TOL).any()) and not bool(_bad(e_w, TOL).any())
+    assert not bool((_bad(e_cpu, TOL) & ~ref_split).any())
 
 
 def test_fast_mode_psnr(golden_dir):
@@ -117,18 +147,26 @@ def test_fast_mode_psnr(golden_dir):
 
 
 def test_oracle_live_vs_cuda_fresh_seed():
-    """Not a fixture: CPU oracle and CUDA path on a fresh seeded case."""
+    """Not a fixture: CPU oracle, oracle-on-cuda and the CUDA path on a fresh seeded case (same contract as
+    test_render_end_to_end)."""
     cfg = dict(H=32, W=32, NV=4, SB=1, near=1.0, far=2.5, K=24, C=300, G=9, white=True, nr=64, seed=21)
     batch, latent, mlp, rays, noise = MG.case_inputs(cfg)
     scene = O.make_scene_state(batch, latent, mlp)
-    rgb_o, depth_o, w_o, z_o = O.render(scene, rays, cfg["K"], cfg["C"], cfg["G"], cfg["white"],
-                                        noise["u_coarse"], noise["g_noise"], noise["u_fill"], return_z=True)
-    model = product_model(batch, latent, mlp, "cuda", "fp32")
-    rend = renderer_for(cfg, noise)
+    rgb_o, depth_o, w_o = O.render(scene, rays, cfg["K"], cfg["C"], cfg["G"], cfg["white"],
+                                   noise["u_coarse"], noise["g_noise"], noise["u_fill"])
+    sc = oracle_scene_on(scene, "cuda")
+    nz = {k: v.cuda() for k, v in noise.items()}
     with torch.no_grad():
-        out = rend(model, rays.cuda())
-    e = torch.maximum((out.fine.rgb.cpu() - rgb_o).abs().max(dim=-1).values, (out.fine.depth.cpu() - depth_o).abs())
-    assert (e > TOL).float().mean() <= 0.02
+        rgb_c, depth_c, _ = O.render(sc, rays.cuda(), cfg["K"], cfg["C"], cfg["G"], cfg["white"], nz["u_coarse"], nz["g_noise"], nz["u_fill"])
+    ref_split = _bad(ray_err(rgb_c.cpu(), depth_c.cpu(), rgb_o, depth_o), TOL)
+    for mode in ("fp32", "parity"):
+        model = product_model(batch, latent, mlp, "cuda", mode)
+        rend = renderer_for(cfg, noise)
+        with torch.no_grad():
+            out = rend(model, rays.cuda())
+        assert not bool(_bad(ray_err(out.fine.rgb, out.fine.depth, rgb_c, depth_c), TOL).any())
+        e = ray_err(out.fine.rgb.cpu(), out.fine.depth.cpu(), rgb_o, depth_o)
+        assert not bool((_bad(e, TOL) & ~ref_split).any())
 
 
 def test_properties_and_edges():
@@ -169,9 +207,10 @@ def test_properties_and_edges():
 
 
 def test_full_size_properties():
-    """BASELINE.json configs[1] at full size (512x512, 4 views, 64 samples/ray, 262 144 rays) through
-    size-independent properties: determinism, shard-vs-whole equality, white/black background relation,
-    weights in [0,1], and parity-mode vs fp32-mode agreement (1e-4) on a strided subset of the rays."""
+    """BASELINE.json configs[1] at full size (512x512, 4 views, 64 samples/ray, 262 144 rays): size-independent
+    properties (determinism, shard-vs-whole equality, white/black background relation, weights in [0,1]) and, on a
+    strided subset of 2048 rays, the tcgen05 parity mode against the fp32 CUDA-core mode AND against the oracle
+    (torch-CPU, and eager torch on cuda) on the same sample depths."""
     import bench
     batch, latent, mlp, rays = bench.build_inputs()
     model = product_model(batch, latent, mlp, "cuda", "parity")
@@ -196,7 +235,18 @@ def test_full_size_properties():
         w_f, rgb_f, d_f = ctx.composite(r_sub, z_sub, False, 0)           # fp32 CUDA-core arithmetic
         e = max(float((rgb_p - rgb_f).abs().max()), float((d_p - d_f).abs().max()))
         print("full-size: parity vs fp32 on 2048 strided rays: max |err| %.3g" % e)
-        assert e <= TOL
+        assert e <= PAR_TOL
+        # ... and against the ORACLE on the same rays and sample depths: on the host cores (the CPU reference path) and on cuda
+        scene = O.make_scene_state(batch, latent, mlp)
+        _, rgb_o, d_o = O.composite(scene, r_sub.cpu(), z_sub.cpu(), False)
+        sc = oracle_scene_on(scene, "cuda")
+        _, rgb_c, d_c = O.composite(sc, r_sub, z_sub, False)
+        e_o = float(ray_err(rgb_p.cpu(), d_p.cpu(), rgb_o, d_o).max())
+        e_c = float(ray_err(rgb_p, d_p, rgb_c, d_c).max())
+        print("full-size: parity vs CPU oracle %.3g, vs oracle-on-cuda %.3g (2048 strided rays, 512x512 workload, 320x320 latent); "
+              "PSNR vs CPU oracle %.1f dB" % (e_o, e_c, O.psnr(rgb_p.cpu(), rgb_o)))
+        assert e_o <= PAR_TOL and e_c <= PAR_TOL
+        del sc
         assert float(w_p.min()) >= 0.0 and float(w_p.sum(-1).max()) <= 1.0 + 1e-5
         w_w, rgb_w, _ = ctx.composite(r_sub, z_sub, True, 1)
         assert (rgb_w - (rgb_p + 1 - w_p.sum(-1, keepdim=True))).abs().max() <= 2e-6
@@ -248,7 +298,7 @@ def test_whole_image_entry_matches_ray_batches():
     _, rgb_p, depth_p = ctx.composite(rays_dev[:, sub].contiguous(), z[:, sub].contiguous(), cfg["white"], 1)
     e = max(float((rgb_p.cpu() - rgb_o).abs().max()), float((depth_p.cpu() - depth_o).abs().max()))
     print("whole-image entry: composite vs oracle on 512 rays/scene: max |err| %.3g" % e)
-    assert e <= TOL
+    assert e <= PAR_TOL
 
 
 @pytest.mark.parametrize("H,W,seed", [(64, 64, 1), (48, 64, 3), (96, 128, 5)])
@@ -300,7 +350,7 @@ def test_other_config_shapes_forward(name, cfg):
     _, rgb_o, d_o = O.composite(scene, rays[:, sub], z[:, sub].cpu(), cfg["white"])
     eo = max(float((rgb_p[:, sub].cpu() - rgb_o).abs().max()), float((d_p[:, sub].cpu() - d_o).abs().max()))
     print("%s: parity vs fp32 max |err| %.3g; parity vs CPU oracle (24 rays/scene) %.3g" % (name, e, eo))
-    assert e <= TOL and eo <= TOL
+    assert e <= PAR_TOL and eo <= PAR_TOL
     assert float(w_p.min()) >= 0.0 and float(w_p.sum(-1).max()) <= 1.0 + 1e-5
 
 
@@ -327,17 +377,18 @@ def test_pair_kernel_pipeline_shape_sweep(NV, SB, K, nr):
     _, rgb_f, d_f = ctx.composite(rays, z, True, 0, want_weights=False)
     e_rgb, e_d = float((rgb_p - rgb_f).abs().max()), float((d_p - d_f).abs().max())
     print("NV=%d SB=%d K=%d rays=%d: parity vs fp32 max |err| rgb %.3g depth %.3g" % (NV, SB, K, nr, e_rgb, e_d))
-    # This test is about the kernel protocol; the 1e-4 bar proper is asserted on the reference goldens and the end-to-end tests.
-    # Depth is a sigma-weighted sum over few, widely spaced samples here (K as low as 8 on random-weight MLPs with a large sigma
-    # gain), which amplifies the ~3e-5 relative error of the bf16x3 pre-activations: allow 2e-4 on depth in this sweep.
-    assert e_rgb <= TOL and e_d <= 2 * TOL
+    # (round 1 measured 1.09e-4 on depth at NV=4 / SB=2 / K=24 with bf16 hi/lo operands -- few, widely spaced samples amplify
+    # the pre-activation error; the fp16 hi/lo split keeps 22 significant bits and is held to PAR_TOL here like everywhere)
+    assert bool(torch.isfinite(rgb_p).all()) and bool(torch.isfinite(d_p).all())
+    assert e_rgb <= PAR_TOL and e_d <= PAR_TOL
     _, rgb_s, _ = ctx.composite(rays, z, True, 2, want_weights=False)       # fast mode runs the same protocol with other timings
-    assert bool(torch.isfinite(rgb_s).all()) and float((rgb_s - rgb_f).abs().max()) < 5e-2
+    assert bool(torch.isfinite(rgb_s).all()) and float((rgb_s - rgb_f).abs().max()) < 1e-2
+    for tail in (0, 4):                                                     # the other MMA issue orders must give the same bits
+        ctx.set_option("tail_kb", tail)
+        _, rgb_t, d_t = ctx.composite(rays, z, True, 1, want_weights=False)
+        assert torch.equal(rgb_t, rgb_p) and torch.equal(d_t, d_p), "tail_kb=%d changes the result" % tail
 
 
-@pytest.mark.skipif(os.environ.get("DINER_B200_EXPERIMENTAL_BACKWARD") != "1",
-                    reason="experimental fp32 backward (diner_render_backward) is not validated on hardware yet; "
-                           "set DINER_B200_EXPERIMENTAL_BACKWARD=1 to run")
 def test_backward_matches_reference_gradients(golden_dir):
     """BASELINE config 3 groundwork: diner_render_backward against loss / gradient digests of the UNMODIFIED reference
     (tests/golden/grads_cfg1_face64.pt, autograd through composite / PixelNeRF.forward / ResnetFC with the MSE of diner.py:266)."""
@@ -370,11 +421,6 @@ def test_backward_matches_reference_gradients(golden_dir):
     check("latent", dl, g["latent_grad"], 4096)
 
 
-_BWD_GATED = pytest.mark.skipif(os.environ.get("DINER_B200_EXPERIMENTAL_BACKWARD") != "1",
-                                reason="experimental fp32 backward: set DINER_B200_EXPERIMENTAL_BACKWARD=1 to run")
-
-
-@_BWD_GATED
 @pytest.mark.parametrize("cfg", [
     dict(H=32, W=48, NV=2, SB=2, near=1.0, far=2.5, K=12, C=100, G=4, white=False, nr=40, seed=32),
     dict(H=32, W=32, NV=8, SB=1, near=1.0, far=2.5, K=16, C=100, G=5, white=True, nr=64, seed=33),
@@ -411,7 +457,6 @@ def test_backward_other_shapes_vs_oracle_autograd(cfg):
     assert scale > 0 and float((dl.cpu() - leaf_lat.grad).abs().max()) / scale <= 5e-3
 
 
-@_BWD_GATED
 def test_training_step_through_module_api(golden_dir):
     """The module-level path a training step takes (diner.py:257-266): NeRFRendererDGS.forward with grad enabled ->
     autograd Function -> loss.backward() fills .grad of the ResnetFC parameters and of encoder.latent."""
@@ -435,7 +480,6 @@ def test_training_step_through_module_api(golden_dir):
     assert lg is not None and abs(float(lg.double().norm()) - g["latent_grad"]["norm"]) <= 0.05 * g["latent_grad"]["norm"]
 
 
-@_BWD_GATED
 def test_training_steps_reduce_the_loss():
     """A few Adam steps (diner.py:333) through calc_losses on a fixed tiny scene must reduce the MSE."""
     from diner_b200 import synthetic as S
@@ -459,15 +503,33 @@ def test_training_steps_reduce_the_loss():
     assert losses[-1] < losses[0]
 
 
-@pytest.mark.skipif(os.environ.get("DINER_B200_EXTRA_CASES") != "1",
-                    reason="oracle-only goldens (K=128/256): not validated on hardware yet; set DINER_B200_EXTRA_CASES=1 to run")
-@pytest.mark.parametrize("name", list(MG.EXTRA_CASES))
-@pytest.mark.parametrize("mode", ["fp32", "parity"])
-def test_extra_cases_composite_stagewise(golden_dir, name, mode):
-    """The K=128 (SB=2) and K=256 (NV=8) reference goldens through the CUDA path, stage-wise on the reference's sample depths."""
-    g, cfg, batch, latent, mlp, rays, noise = _load(golden_dir, name)
-    model = product_model(batch, latent, mlp, "cuda", mode)
-    w, rgb, depth = model.context().composite(rays.cuda(), g["z_filled"].cuda().contiguous(), cfg["white"], model.mode_id())
-    e = max(float((rgb.cpu() - g["rgb"]).abs().max()), float((depth.cpu() - g["depth"]).abs().max()))
-    print("%s/%s: max |err| vs reference %.3g" % (name, mode, e))
-    assert e <= TOL
+def test_render_host_entry_matches_device_entry():
+    """diner_render_host (plain host buffers in and out, copies and the stream sync inside the call -- the entry a non-torch
+    caller binds) must return exactly what diner_render returns for the same rays and seed."""
+    cfg = dict(H=32, W=32, NV=4, SB=2, near=1.0, far=2.5, K=32, C=200, G=12, white=True, nr=300, seed=8)
+    batch, latent, mlp, rays, _ = MG.case_inputs(cfg)
+    model = product_model(batch, latent, mlp, "cuda", "parity")
+    ctx = model.context()
+    SB, NR = rays.shape[:2]
+    rays_h = rays.contiguous()                                    # ordinary pageable host memory
+    rgb_h, dep_h = torch.full((SB, NR, 3), float("nan")), torch.full((SB, NR), float("nan"))
+    ctx.render_host(rays_h, cfg["K"], cfg["C"], cfg["G"], cfg["white"], 1, 4242, rgb_h, dep_h)
+    rgb_d, dep_d, _, _ = ctx.render(rays.cuda(), cfg["K"], cfg["C"], cfg["G"], cfg["white"], 1, dict(seed=4242))
+    assert torch.equal(rgb_h, rgb_d.cpu()) and torch.equal(dep_h, dep_d.cpu())
+    assert bool(torch.isfinite(rgb_h).all())
+
+
+def test_mismatched_scene_and_mlp_are_rejected_before_any_launch():
+    """latent channel count / positional-code width that do not match the MLP must fail with DINER_E_INVALID in
+    every mode (the fp32 path used to size its workspace from d_latent and write with the scene's stride)."""
+    from diner_b200 import synthetic as S
+    cfg = dict(H=32, W=32, NV=2, SB=1, near=1.0, far=2.5, K=8, C=50, G=2, white=True, nr=8, seed=2)
+    batch, latent, mlp, rays, _ = MG.case_inputs(cfg)
+    model = product_model(batch, latent, mlp, "cuda", "fp32")
+    enc = model.encoder
+    enc.set_scene(torch.cat((enc.latent, enc.latent), dim=2).contiguous(), enc.depths, enc.depths_std, enc.normals)   # 1024 channels
+    for mode in ("fp32", "parity", "fast"):
+        model.mode = mode
+        with pytest.raises(RuntimeError, match="latent channels"):
+            with torch.no_grad():
+                renderer_for(cfg)(model, rays.cuda())

@@ -25,7 +25,17 @@ def _worker(rank, world, port, n_rays, q):
     rays = torch.randn(2, n_rays, 8, generator=g)
     rgb, depth = render_sharded(_fake_render, rays)
     ref_rgb, ref_depth = _fake_render(rays)
-    q.put((rank, bool(torch.equal(rgb, ref_rgb) and torch.equal(depth, ref_depth)), tuple(rgb.shape)))
+    ok = bool(torch.equal(rgb, ref_rgb) and torch.equal(depth, ref_depth))
+
+    def packed(r, out):                                   # the zero-copy contract: write (SB,n,4) into the gather slice
+        c, d = _fake_render(r)
+        out[..., :3] = c
+        out[..., 3] = d
+    for rr in (rays, rays[:1].contiguous()):              # SB = 2 and the SB = 1 fast path (views of the gather buffer)
+        rgb_p, depth_p = render_sharded(packed, rr, packed=True)
+        c, d = _fake_render(rr)
+        ok = ok and bool(torch.equal(rgb_p, c) and torch.equal(depth_p, d))
+    q.put((rank, ok, tuple(rgb.shape)))
     dist.destroy_process_group()
 
 
