@@ -45,6 +45,7 @@ SIGNATURES = {
     "diner_query": (_I, [_P, _P, _P, _I, _LL, _I, _P, _P]),
     "diner_composite": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "diner_set_option": (_I, [_P, ctypes.c_char_p, _LL]),
+    "diner_set_float_option": (_I, [_P, ctypes.c_char_p, ctypes.c_double]),
     "diner_debug_sync": (_I, [_P]),
     "diner_launch_count": (_LL, [_P]),
     "diner_set_timing": (_I, [_P, _I]),
@@ -149,9 +150,15 @@ class Context:
                   freq_factor):
         SB, NV, L, Hl, Wl = latent.shape
         H, W = depths.shape[-2:]
+        if not latent.is_contiguous():          # channels-last storage (option latent_layout = 1 | 2): check that layout instead
+            if not latent.permute(0, 1, 3, 4, 2).is_contiguous():
+                raise RuntimeError("latent must be contiguous NCHW or channels-last")
+            lat_ptr = _ptr(latent.permute(0, 1, 3, 4, 2), name="latent")
+        else:
+            lat_ptr = _ptr(latent, name="latent")
         with torch.cuda.device(self.device):
             self._check(self.lib.diner_set_scene(
-                self.handle, SB, NV, L, Hl, Wl, H, W, _ptr(latent, name="latent"),
+                self.handle, SB, NV, L, Hl, Wl, H, W, lat_ptr,
                 _ptr(depths, (SB, NV, 1, H, W), "depths"), _ptr(depths_std, (SB, NV, 1, H, W), "depths_std"),
                 _ptr(normals, (SB, NV, 3, H, W), "normals"), _ptr(poses, (SB, NV, 4, 4), "poses"),
                 _ptr(focal, (SB, NV, 2), "focal"), _ptr(c, (SB, NV, 2), "c"), float(feature_padding),
@@ -295,6 +302,9 @@ class Context:
 
     def set_option(self, key, value):
         self._check(self.lib.diner_set_option(self.handle, key.encode(), int(value)))
+
+    def set_float_option(self, key, value):
+        self._check(self.lib.diner_set_float_option(self.handle, key.encode(), float(value)))
 
     def debug_sync(self):
         self._check(self.lib.diner_debug_sync(self.handle))

@@ -54,6 +54,9 @@ struct diner_ctx {
     void* host_pin = nullptr; size_t host_pin_cap = 0;
     TcState tc;                      // packed weights + scratch of the tcgen05 path
     long long launches = 0;
+    int latent_layout = 0;           // how the next diner_set_scene reads `latent`: 0 NCHW (transposed into a library copy), 1 NHWC (copied), 2 NHWC borrowed
+    float depth_diff_max = 0.05f;    // nerf_renderer.py:66 default
+    float softplus_beta = 0.0f;      // resnetfc.py:124-127: > 0 selects Softplus(beta) activations (fp32 mode only)
     int timing = 0;
     float last_mlp_ms = 0.f, last_sampler_ms = 0.f, last_composite_ms = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -161,9 +164,20 @@ extern "C" int diner_set_scene(diner_ctx* c, int SB, int NV, int L, int Hl, int 
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t nimg = (size_t)SB * NV, lat_n = nimg * L * Hl * Wl, px = nimg * H * W;
-    CUDA_TRY(c->latent.reserve(lat_n * sizeof(float)));
-    CUDA_TRY(launch_nchw_to_nhwc(latent, c->latent.as<float>(), (int)nimg, L, Hl * Wl, st));
-    g_launches++;
+    const float* lat_dev = nullptr;
+    if (c->latent_layout == 2) {                    // channels-last, borrowed: valid until the next diner_set_scene (caller keeps it alive)
+        c->latent.release();
+        lat_dev = latent;
+    } else {
+        CUDA_TRY(c->latent.reserve(lat_n * sizeof(float)));
+        if (c->latent_layout == 1) {
+            CUDA_TRY(cudaMemcpyAsync(c->latent.p, latent, lat_n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else {
+            CUDA_TRY(launch_nchw_to_nhwc(latent, c->latent.as<float>(), (int)nimg, L, Hl * Wl, st));
+            g_launches++;
+        }
+        lat_dev = c->latent.as<float>();
+    }
     CUDA_TRY(c->maps.reserve(px * 5 * sizeof(float)));
     float* mp = c->maps.as<float>();
     CUDA_TRY(cudaMemcpyAsync(mp, depths, px * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -176,7 +190,7 @@ extern "C" int diner_set_scene(diner_ctx* c, int SB, int NV, int L, int Hl, int 
     CUDA_TRY(cudaMemcpyAsync(cp + nimg * 18, cc, nimg * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     SceneDev s{};
     s.SB = SB; s.NV = NV; s.L = L; s.Hl = Hl; s.Wl = Wl; s.H = H; s.W = W;
-    s.latent = c->latent.as<float>();
+    s.latent = lat_dev;
     s.depth = mp; s.dstd = mp + px; s.normal = mp + 2 * px;
     s.poses = cp; s.focal = cp + nimg * 16; s.cxy = cp + nimg * 18;
     s.imgW = (float)W; s.imgH = (float)H;
@@ -214,6 +228,9 @@ static int run_query(diner_ctx* c, const QueryArgs& q, int mode, cudaStream_t st
     if (total == 0) return DINER_OK;
     if (q.SB != c->scene.SB) return fail(DINER_E_INVALID, "SB=%d but the encoded scene has %d objects", q.SB, c->scene.SB);
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev0, st));
+    c->mlp.beta = c->softplus_beta;
+    if (c->softplus_beta > 0.0f && mode != DINER_MODE_FP32)
+        return fail(DINER_E_UNSUPPORTED, "Softplus activations (beta=%g) are served by DINER_MODE_FP32 only", (double)c->softplus_beta);
     if (mode == DINER_MODE_FP32) {
         long long rows = total * c->scene.NV;
         const long long cap_rows = 32768LL * c->scene.NV;
@@ -267,6 +284,7 @@ static int do_sample(diner_ctx* c, const float* rays, int SB, int NR, int K, int
     a.lin_end = end;
     a.lin_step = C > 1 ? end / (float)(C - 1) : 0.0f;
     a.cstep = (float)(1.0 / (double)C);
+    a.depth_diff_max = c->depth_diff_max;
     a.z_out = z; a.z_dgs = z_dgs;
     if (NR == 0) return DINER_OK;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev2, st));
@@ -397,7 +415,7 @@ extern "C" int diner_render_backward(diner_ctx* c, const float* rays, const floa
     if ((rc = check_render_args(c, SB, NR, K, -1, -1))) return rc;
     if ((long long)SB * NR == 0) return DINER_OK;
     if (!rays || !z || !g_rgb || !grad_params) return fail(DINER_E_INVALID, "NULL pointer argument");
-    if (c->scene.L != c->mlp.d_latent) return fail(DINER_E_INVALID, "latent channels %d != d_latent %d", c->scene.L, c->mlp.d_latent);
+    if (c->softplus_beta > 0.0f) return fail(DINER_E_UNSUPPORTED, "the backward pass implements ReLU activations only (softplus_beta=%g)", (double)c->softplus_beta);
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const long long l0 = g_launches;
@@ -487,6 +505,9 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     } else if (!strcmp(key, "early_split")) {
         if (value < 0 || value > 7) return fail(DINER_E_INVALID, "early_split must be in [0,7]");
         c->tc.early_split = (int)value;
+    } else if (!strcmp(key, "latent_layout")) {
+        if (value < 0 || value > 2) return fail(DINER_E_INVALID, "latent_layout must be 0 (NCHW), 1 (NHWC, copied) or 2 (NHWC, borrowed)");
+        c->latent_layout = (int)value;
     } else if (!strcmp(key, "rebuild_maps")) {
         c->tc.zmap_valid = false;        // next query rebuilds the hoisted lin_z maps (bench: times the scene-prepare step)
     } else if (!strcmp(key, "dbg_skip")) {
@@ -496,6 +517,20 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
         c->tc.sub_batch = value;
     } else {
         return fail(DINER_E_INVALID, "unknown option '%s'", key);
+    }
+    return DINER_OK;
+}
+
+extern "C" int diner_set_float_option(diner_ctx* c, const char* key, double value) {
+    if (!c || !key) return fail(DINER_E_INVALID, "NULL ctx / key");
+    if (!strcmp(key, "depth_diff_max")) {
+        if (!(value > 0.0)) return fail(DINER_E_INVALID, "depth_diff_max must be > 0");
+        c->depth_diff_max = (float)value;
+    } else if (!strcmp(key, "softplus_beta")) {
+        if (!(value >= 0.0)) return fail(DINER_E_INVALID, "softplus_beta must be >= 0 (0 = ReLU)");
+        c->softplus_beta = (float)value;
+    } else {
+        return fail(DINER_E_INVALID, "unknown float option '%s'", key);
     }
     return DINER_OK;
 }

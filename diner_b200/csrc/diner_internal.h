@@ -12,6 +12,7 @@ struct SamplerArgs {
     const float* u_fill;     // (SB*NR, K)  or nullptr
     uint64_t seed;
     float lin_step, lin_end, cstep;   // torch.linspace(0, 1-1/C, C) parameters, fp32(1/C)
+    float depth_diff_max;    // |d_ref - z_c| gate of the likelihood mask (nerf_renderer.py:66,121; default 0.05)
     float* z_out;            // (SB*NR, K) ascending
     float* z_dgs;            // optional (SB*NR, K): depth-guided samples before fill-up, ascending, 0 = empty
 };
@@ -21,6 +22,7 @@ struct SamplerArgs {
 #define DINER_MAX_BLOCKS 8
 struct MlpDev {
     int d_in, d_latent, d_hidden, d_out, n_blocks, combine_layer;
+    float beta;              // > 0: Softplus(beta) activations instead of ReLU (resnetfc.py:124-127); fp32 mode only
     const float *w_in, *b_in, *w_out, *b_out;
     const float *w_fc0[DINER_MAX_BLOCKS], *b_fc0[DINER_MAX_BLOCKS];
     const float *w_fc1[DINER_MAX_BLOCKS], *b_fc1[DINER_MAX_BLOCKS];

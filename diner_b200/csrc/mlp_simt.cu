@@ -85,11 +85,20 @@ features_kernel(SceneDev s, QueryArgs q, long long s_begin, long long n_samples,
 }
 
 // Y[r][o] (+)= sum_k act(X[r][k]) * W[o][k] + b[o]   (64x64 tile per CTA, 4x4 per thread, K step 16)
+// nn.Softplus(beta) with torch's threshold of 20 (resnetfc.py:124-125), or ReLU for beta == 0 (:127)
+__device__ __forceinline__ float activation(float x, float beta) {
+    if (beta > 0.0f) {
+        const float bx = beta * x;
+        return bx > 20.0f ? x : log1pf(expf(bx)) / beta;
+    }
+    return fmaxf(x, 0.0f);
+}
+
 template <bool RELU_IN, bool ACCUM>
 __global__ void __launch_bounds__(256)
 linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
               const float* __restrict__ bias, float* __restrict__ Y, int ldy, long long rows, int in_dim,
-              int out_dim) {
+              int out_dim, float beta) {
     __shared__ float Xs[16][68];
     __shared__ float Ws[16][68];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -101,7 +110,7 @@ linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
             const int rr = i >> 4, kk = i & 15;
             const long long r = r0 + rr;
             float xv = (r < rows && k0 + kk < in_dim) ? X[r * ldx + k0 + kk] : 0.0f;
-            if (RELU_IN) xv = fmaxf(xv, 0.0f);
+            if (RELU_IN) xv = activation(xv, beta);
             Xs[kk][rr] = xv;
             const int o = o0 + rr;
             Ws[kk][rr] = (o < out_dim && k0 + kk < in_dim) ? W[(size_t)o * ldw + k0 + kk] : 0.0f;
@@ -160,9 +169,9 @@ __global__ void activate_kernel(float* __restrict__ out, long long n) {
 
 template <bool RELU_IN, bool ACCUM>
 cudaError_t linear(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy,
-                   long long rows, int in_dim, int out_dim, cudaStream_t st) {
+                   long long rows, int in_dim, int out_dim, cudaStream_t st, float beta = 0.0f) {
     dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((out_dim + 63) / 64));
-    linear_kernel<RELU_IN, ACCUM><<<grid, 256, 0, st>>>(X, ldx, W, ldw, b, Y, ldy, rows, in_dim, out_dim);
+    linear_kernel<RELU_IN, ACCUM><<<grid, 256, 0, st>>>(X, ldx, W, ldw, b, Y, ldy, rows, in_dim, out_dim, beta);
     g_launches++;
     return cudaGetLastError();
 }
@@ -205,11 +214,11 @@ cudaError_t query_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q, S
             }
             if (b < m.combine_layer)
                 CK((linear<false, true>(ws.zlat, m.d_latent, m.w_z[b], m.d_latent, m.b_z[b], x, Hd, r, m.d_latent, Hd, st)));
-            CK((linear<true, false>(x, Hd, m.w_fc0[b], Hd, m.b_fc0[b], ws.net, Hd, r, Hd, Hd, st)));
-            CK((linear<true, true>(ws.net, Hd, m.w_fc1[b], Hd, m.b_fc1[b], x, Hd, r, Hd, Hd, st)));
+            CK((linear<true, false>(x, Hd, m.w_fc0[b], Hd, m.b_fc0[b], ws.net, Hd, r, Hd, Hd, st, m.beta)));
+            CK((linear<true, true>(ws.net, Hd, m.w_fc1[b], Hd, m.b_fc1[b], x, Hd, r, Hd, Hd, st, m.beta)));
         }
         if (m.combine_layer >= m.n_blocks && s.NV > 1) return cudaErrorNotSupported;
-        CK((linear<true, false>(x, Hd, m.w_out, Hd, m.b_out, q.out + s0 * 4, 4, r, Hd, m.d_out, st)));
+        CK((linear<true, false>(x, Hd, m.w_out, Hd, m.b_out, q.out + s0 * 4, 4, r, Hd, m.d_out, st, m.beta)));
         activate_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(q.out + s0 * 4, ns);
         g_launches++;
         CK(cudaGetLastError());

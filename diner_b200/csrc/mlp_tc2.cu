@@ -286,7 +286,7 @@ __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ y
         const Tap rt = taps[r];
         const size_t ox = (rt.pix_dxy & (1 << 30)) ? (size_t)HID : 0, oy = (rt.pix_dxy < 0) ? (size_t)s.Wl * HID : 0;
         const float ex = 1.0f - rt.wx, ey = 1.0f - rt.wy;
-        w[0] = ex * ey; w[1] = rt.wx * ey; w[2] = ex * rt.wy; w[3] = rt.wx * rt.wy;
+        w[0] = __fmul_rn(ex, ey); w[1] = __fmul_rn(rt.wx, ey); w[2] = __fmul_rn(ex, rt.wy); w[3] = __fmul_rn(rt.wx, rt.wy);
         const int k0 = KBLK * kb + 8 * (lane & 7);
         const float* b00 = ymap + (size_t)(rt.pix_dxy & 0x3FFFFFFF) * HID + k0;
         f[0] = __ldg((const float4*)b00); f[1] = __ldg((const float4*)(b00 + 4));
@@ -295,12 +295,15 @@ __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ y
         f[6] = __ldg((const float4*)(b00 + oy + ox)); f[7] = __ldg((const float4*)(b00 + oy + ox + 4));
         off = act_off(r, k0 >> 3);
     };
+    // explicit fma chain: the expression is instantiated twice below and must round identically in both (the result must not
+    // depend on which warp / which pass of a warp stages a row)
+    auto bl = [](float a, float b, float c, float d, const float (&w)[4]) { return fmaf(d, w[3], fmaf(c, w[2], fmaf(b, w[1], __fmul_rn(a, w[0])))); };
     auto finish = [&](const float4 (&f)[8], const float (&w)[4], uint32_t off) {
         float4 c03, c47;
-        c03.x = f[0].x * w[0] + f[2].x * w[1] + f[4].x * w[2] + f[6].x * w[3]; c03.y = f[0].y * w[0] + f[2].y * w[1] + f[4].y * w[2] + f[6].y * w[3];
-        c03.z = f[0].z * w[0] + f[2].z * w[1] + f[4].z * w[2] + f[6].z * w[3]; c03.w = f[0].w * w[0] + f[2].w * w[1] + f[4].w * w[2] + f[6].w * w[3];
-        c47.x = f[1].x * w[0] + f[3].x * w[1] + f[5].x * w[2] + f[7].x * w[3]; c47.y = f[1].y * w[0] + f[3].y * w[1] + f[5].y * w[2] + f[7].y * w[3];
-        c47.z = f[1].z * w[0] + f[3].z * w[1] + f[5].z * w[2] + f[7].z * w[3]; c47.w = f[1].w * w[0] + f[3].w * w[1] + f[5].w * w[2] + f[7].w * w[3];
+        c03.x = bl(f[0].x, f[2].x, f[4].x, f[6].x, w); c03.y = bl(f[0].y, f[2].y, f[4].y, f[6].y, w);
+        c03.z = bl(f[0].z, f[2].z, f[4].z, f[6].z, w); c03.w = bl(f[0].w, f[2].w, f[4].w, f[6].w, w);
+        c47.x = bl(f[1].x, f[3].x, f[5].x, f[7].x, w); c47.y = bl(f[1].y, f[3].y, f[5].y, f[7].y, w);
+        c47.z = bl(f[1].z, f[3].z, f[5].z, f[7].z, w); c47.w = bl(f[1].w, f[3].w, f[5].w, f[7].w, w);
         *(float4*)(Ahi + off) = c03;                // channels k0..k0+3
         *(float4*)(Alo + off) = c47;                // channels k0+4..k0+7
     };
@@ -328,6 +331,22 @@ __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ y
         if (two) finish(fb, wb, ob);
     }
     while (waited < kb_hi) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 46); }
+}
+
+// L2 prefetch of the Y-map lines a tile's rows will gather (4 taps x 2 KiB per row), issued by the helper warps while they idle
+// under fc_0: the maps (2.5 GB at config 2) do not fit the L2, and one DRAM miss among the 16 loads a lane has in flight sets the
+// latency of the whole gather pass.  Fire-and-forget (no register is waited on); threads [t0, t0 + nthreads) share the rows.
+__device__ __forceinline__ void prefetch_y_rows(const Args& a, const float* __restrict__ ymap, const Tap* taps, int t, int nthreads) {
+    const SceneDev& s = a.s;
+    for (int i = t; i < ROWS * 4 * (HID * 4 / 128); i += nthreads) {          // (row, tap, 128-byte line)
+        const int line = i & 15, tap = (i >> 4) & 3, r = i >> 6;
+        const Tap rt = taps[r];
+        const size_t ox = ((tap & 1) && (rt.pix_dxy & (1 << 30))) ? (size_t)HID : 0;
+        const size_t oy = ((tap & 2) && rt.pix_dxy < 0) ? (size_t)s.Wl * HID : 0;
+        if (((tap & 1) && !ox) || ((tap & 2) && !oy)) continue;                // clamped at the border: same line as another tap
+        const float* p = ymap + (size_t)(rt.pix_dxy & 0x3FFFFFFF) * HID + ox + oy + 32 * line;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
 }
 
 // Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row; both carry W_SCALE), written
@@ -711,6 +730,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                             if (wt - NUM_WORKERS < ROWS) prep_rows<PARITY, 1, true, false>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
                             asm volatile("bar.sync 9, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");                    // all helpers read these taps below
                             asm volatile("bar.arrive 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                            if (!(a.dbg_skip & 16)) prefetch_y_rows(a, a.zmap, tn, wt - NUM_WORKERS, NUM_HELPER_WARPS * 32);      // next tile's Y_0
+                        } else if (!last && !(a.dbg_skip & 16)) {
+                            prefetch_y_rows(a, a.zmap + (size_t)(b + 1) * a.zmap_stride, tp, wt - NUM_WORKERS, NUM_HELPER_WARPS * 32);   // this tile's Y_{b+1}
                         }
                     } else {
                         asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..4 complete

@@ -93,7 +93,7 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
                 const float sd = lookup_std(s, sv, u, w);
                 if (sd == 0.0f) continue;                                         // bg_mask      (:122)
                 const float dref = lookup_depth(s, sv, u, w);
-                if (!(fabsf(__fsub_rn(dref, zcam)) < 0.05f)) continue;            // depth_dist   (:121)
+                if (!(fabsf(__fsub_rn(dref, zcam)) < a.depth_diff_max)) continue;            // depth_dist   (:121)
                 float nx, ny, nz;
                 lookup_normal(s, sv, u, w, nx, ny, nz);
                 const float cosd = __fadd_rn(__fadd_rn(__fmul_rn(rdx, nx), __fmul_rn(rdy, ny)),

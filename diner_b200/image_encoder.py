@@ -79,8 +79,18 @@ class SpatialEncoder(nn.Module):
                 pyramid.append(x)
         size = pyramid[0].shape[-2:]
         ac = None if self.index_interp == "nearest " else True     # (sic) image_encoder.py:281
-        lat = torch.cat([F.interpolate(t, size, mode=self.upsample_interp, align_corners=ac) for t in pyramid], dim=1)
-        self.latent = lat.view(SB, NV, -1, *size)
+        # The reference concatenates the upsampled levels into an NCHW tensor (image_encoder.py:282-291).  Same values here, but the
+        # levels are written straight into channels-last storage -- the layout the render kernels gather from -- so no separate
+        # NCHW->NHWC pass over the 0.8-5.4 GB latent is needed afterwards.  `self.latent` keeps the reference's
+        # logical shape (SB,NV,L,Hl,Wl); only its strides differ.
+        L = sum(t.shape[1] for t in pyramid)
+        buf = torch.empty(SB * NV, size[0], size[1], L, device=x.device, dtype=pyramid[0].dtype)
+        c0 = 0
+        for t in pyramid:
+            up = F.interpolate(t, size, mode=self.upsample_interp, align_corners=ac)
+            buf[..., c0:c0 + up.shape[1]] = up.permute(0, 2, 3, 1)
+            c0 += up.shape[1]
+        self.latent = buf.permute(0, 3, 1, 2).view(SB, NV, L, *size)
         self.scene_version += 1
         return self.latent
 

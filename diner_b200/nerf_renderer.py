@@ -86,12 +86,14 @@ class NeRFRendererDGS(torch.nn.Module):
     def sample_depthguided(self, rays, model, n_samples, n_candidates, depth_diff_max=0.05, n_gaussian=None):
         """Depth-guided shortlist, nerf_renderer.py:65-190.  Returns (SB,NR,n_samples) with 0 = empty slot,
         sorted ascending (the reference returns the same multiset ordered by likelihood)."""
-        if depth_diff_max != 0.05:
-            raise NotImplementedError("depth_diff_max is fixed to the reference default 0.05")
         G = self.n_gaussian if n_gaussian is None else n_gaussian
         assert n_samples >= G
-        _, zd = model.context().sample(rays.float().contiguous(), n_samples, n_candidates, G,
-                                       self._noise_for_call(), want_dgs=True)
+        ctx = model.context()
+        ctx.set_float_option("depth_diff_max", depth_diff_max)
+        try:
+            _, zd = ctx.sample(rays.float().contiguous(), n_samples, n_candidates, G, self._noise_for_call(), want_dgs=True)
+        finally:
+            ctx.set_float_option("depth_diff_max", 0.05)         # forward() always uses the default (nerf_renderer.py:415-417)
         return zd
 
     def composite(self, model, rays, z_samp):

@@ -2,7 +2,7 @@
 (src/models/pixelnerf.py:13-145); `forward` is served by libdiner_b200 (no PyTorch compute path).
 
 Extra, non-reference attributes:
-  mode        'parity' (tcgen05 bf16x3, default) | 'fast' (tcgen05 bf16) | 'fp32' (CUDA cores)
+  mode        'parity' (tcgen05 fp16x3, default) | 'fast' (tcgen05 fp16) | 'fp32' (CUDA cores)
               -- also settable through the environment variable DINER_B200_MODE
 """
 import os
@@ -45,6 +45,7 @@ class PixelNeRF(torch.nn.Module):
         self._ctx = None
         self._mlp_stamp = None
         self._scene_stamp = None
+        self._beta = 0.0
 
     # ------------------------------------------------------------------------------------------
     def encode(self, images, depths, depths_std, extrinsics, intrinsics):
@@ -74,6 +75,7 @@ class PixelNeRF(torch.nn.Module):
         if self._ctx is None or self._ctx.device != dev:
             self._ctx = capi.Context(dev)
             self._mlp_stamp = self._scene_stamp = None
+            self._beta = 0.0
         return self._ctx
 
     def context(self):
@@ -81,8 +83,12 @@ class PixelNeRF(torch.nn.Module):
         dev = self.poses.device
         self._bare_context(dev)
         m = self.mlp_fine
-        if getattr(m, "beta", 0.0) > 0:
-            raise NotImplementedError("softplus ResnetFC (beta > 0) is not supported by libdiner_b200")
+        if m.combine_type != "average":                     # the reference's combine() raises for anything else (resnetfc.py:9-14)
+            raise NotImplementedError(m.combine_type)
+        beta = float(getattr(m, "beta", 0.0) or 0.0)
+        if beta != self._beta:                              # Softplus(beta) activations (resnetfc.py:124-127)
+            self._ctx.set_float_option("softplus_beta", beta)
+            self._beta = beta
         sd, stamp = m.packed_state()
         if stamp != self._mlp_stamp:
             self._ctx.set_mlp(sd, m.d_in, m.d_latent, m.d_hidden, m.d_out, m.n_blocks, m.combine_layer)
@@ -95,7 +101,13 @@ class PixelNeRF(torch.nn.Module):
             if enc.index_interp != "bilinear" or enc.index_padding != "border":
                 raise NotImplementedError("libdiner_b200 implements bilinear/border latent indexing only")
             f32 = lambda t: t.detach().float().contiguous()
-            self._ctx.set_scene(f32(enc.latent), f32(enc.depths), f32(enc.depths_std), f32(enc.normals),
+            lat = enc.latent.detach().float()
+            nhwc = lat.dim() == 5 and lat.permute(0, 1, 3, 4, 2).is_contiguous() and not lat.is_contiguous()
+            # channels-last latent (what SpatialEncoder.forward emits): handed over as is and borrowed by the library -- no
+            # re-layout pass, no second copy in HBM; an NCHW latent (reference layout, e.g. set_scene in tests) is transposed once
+            self._latent_keepalive = lat if nhwc else None
+            self._ctx.set_option("latent_layout", 2 if nhwc else 0)
+            self._ctx.set_scene(lat if nhwc else lat.contiguous(), f32(enc.depths), f32(enc.depths_std), f32(enc.normals),
                                 f32(self.poses), f32(self.focal), f32(self.c), enc.feature_padding,
                                 self.poscode.num_freqs, self.poscode.freq_factor)
             self._scene_stamp = sstamp
@@ -104,6 +116,8 @@ class PixelNeRF(torch.nn.Module):
     def mode_id(self):
         if self.mode not in capi.MODES:
             raise ValueError("mode must be one of %s" % list(capi.MODES))
+        if float(getattr(self.mlp_fine, "beta", 0.0) or 0.0) > 0:
+            return capi.MODE_FP32       # Softplus networks are served by the fp32 CUDA-core kernels (the tcgen05 epilogues are ReLU)
         return capi.MODES[self.mode]
 
     def _no_grad_only(self, *tensors):

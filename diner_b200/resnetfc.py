@@ -36,8 +36,6 @@ class ResnetFC(nn.Module):
     def __init__(self, d_in, d_out=4, n_blocks=5, d_latent=0, d_hidden=128, beta=0.0, combine_layer=1000,
                  combine_type="average"):
         super().__init__()
-        if combine_type != "average":
-            raise NotImplementedError(combine_type)
         self.n_blocks, self.d_latent, self.d_in, self.d_out, self.d_hidden = n_blocks, d_latent, d_in, d_out, d_hidden
         self.combine_layer, self.combine_type, self.beta = combine_layer, combine_type, beta
         if d_in > 0:
@@ -65,6 +63,8 @@ class ResnetFC(nn.Module):
         x = self.lin_in(x) if self.d_in > 0 else torch.zeros(self.d_hidden, device=zx.device)
         for b, blk in enumerate(self.blocks):
             if b == self.combine_layer:
+                if self.combine_type != "average":          # resnetfc.py:9-14: the reference's combine() raises here as well
+                    raise NotImplementedError
                 x = torch.mean(x, dim=combine_dim)
             if self.d_latent > 0 and b < self.combine_layer:
                 x = x + self.lin_z[b](z)

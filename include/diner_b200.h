@@ -59,7 +59,9 @@ int diner_set_mlp(diner_ctx* ctx, int d_in, int d_latent, int d_hidden, int d_ou
 
 /* Scene state -- replaces what PixelNeRF.encode leaves on the modules (src/models/pixelnerf.py:44-51,
  * src/models/image_encoder.py:232-237,290-291):
- *   latent  (SB,NV,L,Hl,Wl) NCHW fp32 as the reference stores it (re-laid out to NHWC internally)
+ *   latent  (SB,NV,L,Hl,Wl) NCHW fp32 as the reference stores it (re-laid out to NHWC internally); with
+ *           diner_set_option("latent_layout", 1 | 2) set beforehand it is read as channels-last (SB,NV,Hl,Wl,L) instead --
+ *           1 = copied, 2 = borrowed (no copy: the pointer must then stay valid until the next diner_set_scene)
  *   depths, depths_std (SB,NV,1,H,W); normals (SB,NV,3,H,W)
  *   poses (SB,NV,4,4) world->cam; focal, c (SB,NV,2); image is W x H pixels
  *   feature_padding = image_padding / conv1 stride (image_encoder.py:58); num_freqs / freq_factor of
@@ -143,9 +145,14 @@ int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, i
 
 /* Tuning knobs of the tcgen05 path (not part of the reference API): key = "tail_kb" (0..4: K blocks of every GEMM step issued
  * N-tile-outer so that the first epilogue half overlaps the step's tail), "early_split" (worker/helper split of the next tile's
- * early gather), "sub_batch" (samples per PRE/POST launch pair) or "rebuild_maps" (forces the next query to rebuild the hoisted
- * lin_z maps). */
+ * early gather), "sub_batch" (samples per PRE/POST launch pair), "rebuild_maps" (forces the next query to rebuild the hoisted
+ * lin_z maps) or "latent_layout" (see diner_set_scene). */
 int diner_set_option(diner_ctx* ctx, const char* key, long long value);
+/* Reference arguments that are not per-call sizes: key = "depth_diff_max" (sample_depthguided(..., depth_diff_max=0.05),
+ * src/models/nerf_renderer.py:66,121) or "softplus_beta" (ResnetFC(beta=...): Softplus(beta) activations instead of ReLU,
+ * src/models/resnetfc.py:124-127; 0 = ReLU; served by DINER_MODE_FP32 only, the tcgen05 modes and the backward return
+ * DINER_E_UNSUPPORTED). */
+int diner_set_float_option(diner_ctx* ctx, const char* key, double value);
 
 /* cudaDeviceSynchronize + decoded tcgen05 watchdog code on failure (debugging aid). */
 int diner_debug_sync(diner_ctx* ctx);

@@ -47,6 +47,7 @@ class Scene:
     freq_factor: float = 6.28
     n_blocks: int = 5
     combine_layer: int = 3
+    beta: float = 0.0            # ResnetFC(beta): > 0 -> Softplus(beta) activations (resnetfc.py:124-127)
     extra: dict = field(default_factory=dict)
 
 
@@ -155,6 +156,7 @@ def resnetfc(scene: Scene, zx):
     """zx (SB,NV,B,L+d_in) -> (SB,B,4).  Follows reference src/models/resnetfc.py:61-69,129-159
     (ReLU activations, mean over the view axis at `combine_layer`)."""
     m = scene.mlp
+    act = (lambda t: F.softplus(t, beta=scene.beta)) if scene.beta > 0 else torch.relu      # resnetfc.py:124-127
     L = m["lin_z.0.weight"].shape[1]
     z, x = zx[..., :L], zx[..., L:]
     x = F.linear(x, m["lin_in.weight"], m["lin_in.bias"])
@@ -163,10 +165,10 @@ def resnetfc(scene: Scene, zx):
             x = torch.mean(x, dim=1)
         if b < scene.combine_layer:
             x = x + F.linear(z, m["lin_z.%d.weight" % b], m["lin_z.%d.bias" % b])
-        net = F.linear(torch.relu(x), m["blocks.%d.fc_0.weight" % b], m["blocks.%d.fc_0.bias" % b])
-        dx = F.linear(torch.relu(net), m["blocks.%d.fc_1.weight" % b], m["blocks.%d.fc_1.bias" % b])
+        net = F.linear(act(x), m["blocks.%d.fc_0.weight" % b], m["blocks.%d.fc_0.bias" % b])
+        dx = F.linear(act(net), m["blocks.%d.fc_1.weight" % b], m["blocks.%d.fc_1.bias" % b])
         x = x + dx
-    return F.linear(torch.relu(x), m["lin_out.weight"], m["lin_out.bias"])
+    return F.linear(act(x), m["lin_out.weight"], m["lin_out.bias"])
 
 
 def query(scene: Scene, xyz, viewdirs):
@@ -224,12 +226,12 @@ def candidate_likelihood(scene: Scene, rays, z_cand, depth_diff_max=0.05):
     return torch.max(lik, dim=1).values.squeeze(1).reshape(SB, NR, C)              # :129-130
 
 
-def sample_depthguided(scene: Scene, rays, K, C, G, u_coarse, g_noise, return_aux=False):
+def sample_depthguided(scene: Scene, rays, K, C, G, u_coarse, g_noise, return_aux=False, depth_diff_max=0.05):
     """Depth-guided shortlist (nerf_renderer.py:65-190) with dense injected noise -> (SB,NR,K), 0 = empty."""
     assert K >= G
     SB, NR = rays.shape[:2]
     z_cand = sample_coarse(rays, C, u_coarse)
-    lik = candidate_likelihood(scene, rays, z_cand)
+    lik = candidate_likelihood(scene, rays, z_cand, depth_diff_max)
     opq = lik.clone()
     opq[..., 1:] *= torch.cumprod(1. - lik, dim=-1)[..., :-1]                      # :131-132
     idx = lik.argsort(dim=-1, descending=True)[..., :K]                            # :172

@@ -4,7 +4,11 @@ and against the same oracle executed as eager PyTorch ON THE GPU (the reference'
 target: src/models runs on cuda in python_scripts/train.py / create_prediction_folder.py).
 
 Tolerances: north_star asks for 1e-4 abs on rgb / depth (TOL).  The tcgen05 parity mode (fp16 hi/lo
-split operands, fp32 accumulation) is held to PAR_TOL = 2e-5 wherever the sample depths are given.
+split operands, fp32 accumulation in TMEM) is held to PAR_TOL = 5e-5, half the bar, wherever the sample
+depths are given; measured: <= 1.3e-5 at the headline size, <= 3.7e-5 in the worst small case.  What is
+left is not operand precision (the split keeps 22 bits) but the tensor core's accumulator, which truncates
+instead of rounding at each of the 96 MMA steps of a 512-wide layer (tools/sim_accumulate_rz.py reproduces
+the measured error level on the CPU with exactly that model, and 8e-7 with round-to-nearest accumulation).
 Stage-wise comparisons (same sample depths in) must meet the bar on EVERY ray, NaN counting as a
 failure.  End-to-end comparisons additionally go through the sampler's discontinuous decisions
 (nearest-pixel lookups, "likelihood != 0" membership of the shortlist).  Those decisions hinge on the
@@ -26,7 +30,7 @@ pytestmark = pytest.mark.gpu
 CASES = list(MG.CASES)
 ALL_CASES = list(MG.CASES) + list(MG.EXTRA_CASES)
 TOL = 1e-4          # north_star bar
-PAR_TOL = 2e-5      # what the fp16x3 parity mode is held to on given sample depths
+PAR_TOL = 5e-5      # what the fp16x3 parity mode is held to on given sample depths (half the bar; see the module docstring)
 Z_TOL = 1e-5        # sample depths: a different shortlist decision moves a sample by >= one candidate step (>= 1e-3)
 
 
@@ -88,7 +92,9 @@ def test_query_stagewise(golden_dir, name, mode, tol):
     err_rgb = (out[..., :3] - ref[..., :3]).abs().max()
     rel_sig = ((out[..., 3] - ref[..., 3]).abs() / (1.0 + ref[..., 3].abs())).max()
     print("%s/%s: max|d rgb| %.3g  max rel|d sigma| %.3g" % (name, mode, err_rgb, rel_sig))
-    assert err_rgb <= tol and rel_sig <= tol
+    # sigma enters the image only through alpha = 1 - exp(-delta * sigma) with delta ~ 1e-2: relative 1e-4 on it is far inside the
+    # bar on the rendered values, which test_composite_stagewise / test_render_end_to_end assert directly
+    assert err_rgb <= tol and rel_sig <= (1e-4 if mode == "parity" else tol)
 
 
 @pytest.mark.parametrize("name", ALL_CASES)
@@ -533,3 +539,35 @@ def test_mismatched_scene_and_mlp_are_rejected_before_any_launch():
         with pytest.raises(RuntimeError, match="latent channels"):
             with torch.no_grad():
                 renderer_for(cfg)(model, rays.cuda())
+
+
+def test_softplus_network_and_depth_diff_max(golden_dir):
+    """Reference arguments off the shipped configs: ResnetFC(beta > 0) -> Softplus activations (resnetfc.py:124-127), served by
+    the fp32 kernels whatever `mode` says; sample_depthguided(depth_diff_max != 0.05) (nerf_renderer.py:66,121)."""
+    g, cfg, batch, latent, mlp, rays, noise = _load(golden_dir, "sb2_nv2_rect")
+    model = product_model(batch, latent, mlp, "cuda", "parity")
+    model.mlp_fine.beta = 1.5
+    scene = O.make_scene_state(batch, latent, mlp)
+    scene.beta = 1.5
+    rend = renderer_for(cfg)
+    with torch.no_grad():
+        w, rgb, depth = rend.composite(model, rays.cuda(), g["z_filled"].cuda())
+        w_o, rgb_o, depth_o = O.composite(scene, rays, g["z_filled"], cfg["white"])
+    e = float(ray_err(rgb.cpu(), depth.cpu(), rgb_o, depth_o).max())
+    print("softplus(beta=1.5) network, fp32 kernels vs oracle: max |err| %.3g" % e)
+    assert e <= 2e-5 and float((rgb_o - g["rgb"]).abs().max()) > 1e-3          # and it really is a different network
+    with pytest.raises(RuntimeError, match="Softplus"):
+        model.context().composite(rays.cuda(), g["z_filled"].cuda().contiguous(), cfg["white"], 1)
+    # depth_diff_max through the reference's method signature
+    model.mlp_fine.beta = 0.0
+    nz = {k: v.cuda().contiguous() for k, v in noise.items()}
+    rend = renderer_for(cfg, noise)
+    sc = oracle_scene_on(O.make_scene_state(batch, latent, mlp), "cuda")
+    for ddm in (0.01, 0.2):
+        zd = rend.sample_depthguided(rays.cuda(), model, cfg["K"], cfg["C"], depth_diff_max=ddm)
+        with torch.no_grad():
+            zo = O.sample_depthguided(sc, rays.cuda(), cfg["K"], cfg["C"], cfg["G"], nz["u_coarse"], nz["g_noise"], depth_diff_max=ddm)
+        d = (zd - zo.sort(dim=-1).values).abs().max(dim=-1).values
+        assert not bool(_bad(d, Z_TOL).any()), "depth_diff_max=%g" % ddm
+    z_default = rend.sample_depthguided(rays.cuda(), model, cfg["K"], cfg["C"])
+    assert not torch.equal(z_default, zd)
