@@ -270,7 +270,7 @@ __device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, ui
 // PRE gather: bilinear Y_b (= lin_z[b] of the latent map) rows of a tile -> fp32 staging in the (A_hi, A_lo) chunk slots, for
 // the K blocks [kb_lo, kb_hi], in K-BLOCK ORDER and overlapped with the GEMM that is still reading the operand buffers: before
 // touching K block kb the warp waits on bar_afree[kb], which the MMA issuer commits right after the last MMA that reads it.
-// Every warp waits on every barrier of the range, in order (keeps the phase parities in step): par0 is the parity of
+// A warp waits on the barriers of the K blocks up to its last own one, in order: par0 is the parity of
 // bar_afree[0], par1 that of the others (K block 0 has one more release per tile: it also carries the lin_in features).
 // One pass = 4 rows x 64 channels (one K block): lane -> row 4*(p%16) + lane/8, 8 channels (lane%8): 32-byte loads per tap;
 // channels 0..3 of the chunk go to the hi slot, 4..7 to the lo slot (the epilogue thread that owns the row reads them back).
@@ -330,7 +330,12 @@ __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ y
         finish(fa, wa, oa);
         if (two) finish(fb, wb, ob);
     }
-    while (waited < kb_hi) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 46); }
+    // Helpers pass every barrier of the range (they own its last K blocks anyway).  Workers do NOT wait for the K blocks beyond their
+    // own share: those are released in the N-tile-outer tail of the running GEMM, i.e. at its very end, and the point of the tail
+    // is that the workers' first epilogue half runs under it.  Skipping a phase of bar_afree[kb] is safe for them: before their
+    // next wait on that barrier they pass bar_acc of the step that completes the skipped phase (commits complete in order).
+    if (helper)
+        while (waited < kb_hi) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 46); }
 }
 
 // L2 prefetch of the Y-map lines a tile's rows will gather (4 taps x 2 KiB per row), issued by the helper warps while they idle

@@ -124,3 +124,32 @@ def test_ctypes_signatures_match_header_arity():
         n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
         assert n == len(capi.SIGNATURES[name][1]), "%s: header has %d parameters, ctypes table %d" % (
             name, n, len(capi.SIGNATURES[name][1]))
+
+
+def test_encoder_emits_channels_last_latent_with_reference_values():
+    """SpatialEncoder.forward writes the pyramid levels straight into channels-last storage (scene prepare):
+    logical shape and values as the reference (image_encoder.py:281-291) -- checked live against the unmodified reference encoder
+    when its tree is present, gradients included -- but NHWC strides, which libdiner_b200 borrows without a re-layout pass."""
+    from diner_b200 import synthetic as S
+    from src.models.image_encoder import SpatialEncoder
+    torch.manual_seed(0)
+    enc = SpatialEncoder(pretrained=False, image_padding=64, padding_pe=4).eval()
+    b = S.make_scene(64, 64, 2, 1)
+    nrm = torch.zeros(1, 2, 3, 64, 64)
+    with torch.no_grad():
+        lat = enc(b["src_rgbs"], b["src_depths"], b["src_depth_stds"], nrm)
+    assert lat.shape == (1, 2, 512, 96, 96) and lat.permute(0, 1, 3, 4, 2).is_contiguous() and not lat.is_contiguous()
+    if not os.path.isdir("/root/reference/src"):
+        return
+    from oracle import ref_import
+    ns = ref_import.load()
+    ref = ns.image_encoder.SpatialEncoder(pretrained=False, image_padding=64, padding_pe=4).eval()
+    ref.load_state_dict(enc.state_dict())
+    with torch.no_grad():
+        ref(b["src_rgbs"], b["src_depths"], b["src_depth_stds"], nrm)
+    assert torch.equal(ref.latent, lat)
+    g = S.hash_normal(tuple(lat.shape), 3)
+    (enc(b["src_rgbs"], b["src_depths"], b["src_depth_stds"], nrm) * g).sum().backward()
+    ref(b["src_rgbs"], b["src_depths"], b["src_depth_stds"], nrm)
+    (ref.latent * g).sum().backward()
+    assert torch.equal(enc.model.conv1.weight.grad, ref.model.conv1.weight.grad)

@@ -571,3 +571,26 @@ def test_softplus_network_and_depth_diff_max(golden_dir):
         assert not bool(_bad(d, Z_TOL).any()), "depth_diff_max=%g" % ddm
     z_default = rend.sample_depthguided(rays.cuda(), model, cfg["K"], cfg["C"])
     assert not torch.equal(z_default, zd)
+
+
+def test_encode_path_borrows_channels_last_latent():
+    """PixelNeRF.encode (ResNet-34 trunk on cuDNN, random weights) -> channels-last latent borrowed by the library (no re-layout
+    pass) must render exactly what the reference-layout (NCHW, transposed once) hand-over renders."""
+    from diner_b200 import synthetic as S
+    cfg = dict(H=64, W=64, NV=3, SB=2, near=1.0, far=2.5, K=24, C=200, G=8, white=True, nr=500, seed=13)
+    batch, latent, mlp, rays, _ = MG.case_inputs(cfg)
+    torch.manual_seed(1)
+    model = product_model(batch, latent, mlp, "cuda", "parity")
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    with torch.no_grad():
+        model.encode(b["src_rgbs"], b["src_depths"], b["src_depth_stds"], b["src_extrinsics"], b["src_intrinsics"])
+        lat = model.encoder.latent
+        assert not lat.is_contiguous() and lat.permute(0, 1, 3, 4, 2).is_contiguous()
+        rend = renderer_for(cfg)
+        rend.noise = dict(seed=5)
+        a = rend(model, rays.cuda())
+        l0 = model.context().launch_count()
+        model.encoder.set_scene(lat.contiguous(), model.encoder.depths, model.encoder.depths_std, model.encoder.normals)   # NCHW copy
+        c = rend(model, rays.cuda())
+    assert torch.equal(a.fine.rgb, c.fine.rgb) and torch.equal(a.fine.depth, c.fine.depth)
+    assert bool(torch.isfinite(a.fine.rgb).all()) and float(a.fine.rgb.std()) > 0
