@@ -324,8 +324,8 @@ def main():
     rays_dev = rays_host.to(dev)
     ctx = model.context()
 
-    def packed_render(r, out):
-        rend.render_packed(model, r, out=out)           # compositing kernel writes rgb|depth into the gather slice
+    def packed_render(r, out, ray_offset):
+        rend.render_packed(model, r, out=out, ray_offset=ray_offset)    # compositing kernel writes rgb|depth into the gather slice
 
     def step(src):
         return render_sharded(packed_render, src, packed=True, return_packed=True)   # one in-place NCCL all-gather per image when world > 1

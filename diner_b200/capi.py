@@ -20,7 +20,7 @@ _c_float_p = ctypes.c_void_p
 
 class DinerNoise(ctypes.Structure):
     _fields_ = [("u_coarse", ctypes.c_void_p), ("g_noise", ctypes.c_void_p), ("u_fill", ctypes.c_void_p),
-                ("seed", ctypes.c_uint64)]
+                ("seed", ctypes.c_uint64), ("ray_offset", ctypes.c_uint64)]
 
 
 # name -> (restype, argtypes); mirrors include/diner_b200.h one to one
@@ -177,6 +177,7 @@ class Context:
                 setattr(n, key, _ptr(t, shape, key).value)
                 keep.append(t)
         n.seed = int(noise.get("seed", 0))
+        n.ray_offset = int(noise.get("ray_offset", 0))
         return n, keep
 
     def render(self, rays, K, C, G, white_bkgd, mode, noise=None, want_weights=False, want_z=False):

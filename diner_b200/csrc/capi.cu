@@ -280,6 +280,7 @@ static int do_sample(diner_ctx* c, const float* rays, int SB, int NR, int K, int
     a.g_noise = noise ? noise->g_noise : nullptr;
     a.u_fill = noise ? noise->u_fill : nullptr;
     a.seed = noise ? noise->seed : 0;
+    a.ray_offset = noise ? noise->ray_offset : 0;
     const float end = (float)(1.0 - 1.0 / (double)C);          // torch.linspace(0, 1 - step, C)
     a.lin_end = end;
     a.lin_step = C > 1 ? end / (float)(C - 1) : 0.0f;
@@ -488,7 +489,7 @@ extern "C" int diner_render_host(diner_ctx* c, const float* rays_host, int SB, i
     CUDA_TRY(cudaMemcpyAsync(c->rays_dev.p, rays_host, n * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
     float* rgb = c->out_dev.as<float>();
     float* dep = rgb + n * 3;
-    diner_noise nz{nullptr, nullptr, nullptr, seed};
+    diner_noise nz{nullptr, nullptr, nullptr, seed, 0};
     rc = diner_render(c, c->rays_dev.as<float>(), SB, NR, K, C, G, white_bkgd, mode, &nz, rgb, dep, nullptr, nullptr, stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(rgb_host, rgb, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -10,7 +10,7 @@ struct SamplerArgs {
     const float* u_coarse;   // (SB*NR, C)  or nullptr -> counter-based noise from `seed`
     const float* g_noise;    // (SB*NR, G)  or nullptr
     const float* u_fill;     // (SB*NR, K)  or nullptr
-    uint64_t seed;
+    uint64_t seed, ray_offset;   // counter-based noise: key and logical index of the call's first ray (per scene)
     float lin_step, lin_end, cstep;   // torch.linspace(0, 1-1/C, C) parameters, fp32(1/C)
     float depth_diff_max;    // |d_ref - z_c| gate of the likelihood mask (nerf_renderer.py:66,121; default 0.05)
     float* z_out;            // (SB*NR, K) ascending

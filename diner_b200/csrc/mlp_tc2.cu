@@ -116,7 +116,8 @@ struct Args {
     GemmStep steps[MAX_STEPS];
     int n_steps, n_blocks, uses_per_tile;
     long long s_begin, n_samples, n_total, n_tiles;   // n_tiles counts 64-row CTA tiles
-    int NV, spv;
+    int NV, spv;                // NV = views per sample padded to a power of two (rows of a sample are NV adjacent rows), spv = 64 / NV
+    int NV_real;                // the scene's view count: rows of the padding views repeat view 0 and are masked out of the combine
     float* xc;                  // [sample][512] fp32 view-combined activations (sub-batch relative)
     float* out;
     float* zmap;                // Y maps [block][pixel][512] fp32: PRE reads them, ZMAP writes them
@@ -225,7 +226,7 @@ __device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, ui
     const int r = wt & 63, part = wt >> 6;
     long long smp = a.s_begin + tile * a.spv + r / a.NV;
     if (smp >= a.n_total) smp = a.n_total - 1;
-    const int v = r % a.NV;
+    const int v = (r % a.NV) < a.NV_real ? (r % a.NV) : 0;          // padding views (view count not a power of two) repeat view 0
     const int sb = (int)(smp / a.q.n_per_sb);
     float px, py, pz, dx, dy, dz;
     sample_point(a.q, smp, px, py, pz, dx, dy, dz);
@@ -338,22 +339,6 @@ __device__ __noinline__ void gather_y(const Args& a, const float* __restrict__ y
         while (waited < kb_hi) { ++waited; mbar_wait(bar_afree + 8 * waited, waited == 0 ? par0 : par1, a.err, 46); }
 }
 
-// L2 prefetch of the Y-map lines a tile's rows will gather (4 taps x 2 KiB per row), issued by the helper warps while they idle
-// under fc_0: the maps (2.5 GB at config 2) do not fit the L2, and one DRAM miss among the 16 loads a lane has in flight sets the
-// latency of the whole gather pass.  Fire-and-forget (no register is waited on); threads [t0, t0 + nthreads) share the rows.
-__device__ __forceinline__ void prefetch_y_rows(const Args& a, const float* __restrict__ ymap, const Tap* taps, int t, int nthreads) {
-    const SceneDev& s = a.s;
-    for (int i = t; i < ROWS * 4 * (HID * 4 / 128); i += nthreads) {          // (row, tap, 128-byte line)
-        const int line = i & 15, tap = (i >> 4) & 3, r = i >> 6;
-        const Tap rt = taps[r];
-        const size_t ox = ((tap & 1) && (rt.pix_dxy & (1 << 30))) ? (size_t)HID : 0;
-        const size_t oy = ((tap & 2) && rt.pix_dxy < 0) ? (size_t)s.Wl * HID : 0;
-        if (((tap & 1) && !ox) || ((tap & 2) && !oy)) continue;                // clamped at the border: same line as another tap
-        const float* p = ymap + (size_t)(rt.pix_dxy & 0x3FFFFFFF) * HID + ox + oy + 32 * line;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-}
-
 // Block entry epilogue (replaces the lin_z GEMM): x' = x (TMEM, fp32) + g (staged bilinear Y_b row; both carry W_SCALE), written
 // back to TMEM as the residual; relu(x') * W_INV -> fp16 hi/lo chunks of the fc_0 operand.  The biases that precede this point (b_in / b_fc1[b-1] and
 // b_z[b]) are folded into Y_b when the maps are built (the four bilinear weights sum to 1), so the residual in TMEM carries them.  Each thread reads and then overwrites
@@ -457,15 +442,18 @@ __device__ __forceinline__ int combine_lanes(float (&v)[32], int lane) {
     return offset;
 }
 template <int NV>
-__device__ __forceinline__ void combine_store(uint32_t* raw, const float* __restrict__ cb, int h0, int lane, float* dst_sample, bool write) {
+__device__ __forceinline__ void combine_store(uint32_t* raw, const float* __restrict__ cb, int h0, int lane, float* dst_sample, bool write,
+                                              int nv_real) {
     float v[32];
+    const bool pad_row = (lane & (NV - 1)) >= nv_real;          // row of a padding view: contributes nothing to the mean
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+    for (int i = 0; i < 32; ++i) v[i] = pad_row ? 0.0f : __uint_as_float(raw[i]);
     const int off = combine_lanes<NV>(v, lane);
     constexpr int CNT = 32 / NV;
     if (write) {
+        const float scale = W_INV / (float)nv_real;
 #pragma unroll
-        for (int i = 0; i < CNT; ++i) v[i] = v[i] * (W_INV / (float)NV) + __ldg(cb + h0 + off + i);
+        for (int i = 0; i < CNT; ++i) v[i] = v[i] * scale + __ldg(cb + h0 + off + i);
         float* dst = dst_sample + h0 + off;
         if constexpr (CNT >= 4) {
 #pragma unroll
@@ -735,9 +723,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                             if (wt - NUM_WORKERS < ROWS) prep_rows<PARITY, 1, true, false>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
                             asm volatile("bar.sync 9, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");                    // all helpers read these taps below
                             asm volatile("bar.arrive 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
-                            if (!(a.dbg_skip & 16)) prefetch_y_rows(a, a.zmap, tn, wt - NUM_WORKERS, NUM_HELPER_WARPS * 32);      // next tile's Y_0
-                        } else if (!last && !(a.dbg_skip & 16)) {
-                            prefetch_y_rows(a, a.zmap + (size_t)(b + 1) * a.zmap_stride, tp, wt - NUM_WORKERS, NUM_HELPER_WARPS * 32);   // this tile's Y_{b+1}
                         }
                     } else {
                         asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..4 complete
@@ -799,12 +784,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
                     const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
                     switch (a.NV) {
-                        case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr); break;
-                        case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr); break;
-                        case 4: combine_store<4>(v, cb, h0, lane, dst_sample, wr); break;
-                        case 8: combine_store<8>(v, cb, h0, lane, dst_sample, wr); break;
-                        case 16: combine_store<16>(v, cb, h0, lane, dst_sample, wr); break;
-                        default: combine_store<32>(v, cb, h0, lane, dst_sample, wr); break;
+                        case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                        case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                        case 4: combine_store<4>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                        case 8: combine_store<8>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                        case 16: combine_store<16>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                        default: combine_store<32>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
                     }
                 }
                 tc_fence_before();
@@ -996,7 +981,7 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
     z.n_steps = t.n_pre;
     z.zmap = t.zmap; z.zmap_stride = n_pix * HID; z.n_pix = n_pix;
     z.n_tiles = (n_pix + ROWS - 1) / ROWS;
-    z.NV = s.NV; z.spv = ROWS / s.NV;
+    z.NV = z.NV_real = 1; z.spv = ROWS;
     z.err = t.err_flag;
     const long long g = ((z.n_tiles + 1) / 2) * 2;
     if (t.timing) TCK(cudaEventRecord(t.ev[0], st));
@@ -1013,8 +998,9 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
 cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity, int num_sms,
                       cudaStream_t st) {
     using namespace tc2;
-    const int NV = s.NV;
-    if (NV > 32 || (32 % NV)) { snprintf(t.why, sizeof(t.why), "NV=%d views (tcgen05 path needs NV in {1,2,4,8,16,32})", NV); return cudaErrorNotSupported; }
+    if (s.NV > 32) { snprintf(t.why, sizeof(t.why), "NV=%d views (the tcgen05 path serves up to 32)", s.NV); return cudaErrorNotSupported; }
+    int NV = 1;                       // rows per sample: the view count padded to a power of two (padding rows are masked out of the mean)
+    while (NV < s.NV) NV *= 2;
     if (s.L != m.d_latent || (s.L % KBLK) || s.L > HID) { snprintf(t.why, sizeof(t.why), "pair kernel needs d_latent == latent channels, %% 64 == 0, <= 512 (got %d / %d)", m.d_latent, s.L); return cudaErrorNotSupported; }
     const int d_in = 3 + 6 * s.num_freqs + 3 + 1 + 2 * s.num_freqs;
     if (d_in != m.d_in) { snprintf(t.why, sizeof(t.why), "positional code gives d_in=%d but lin_in expects %d", d_in, m.d_in); return cudaErrorNotSupported; }
@@ -1065,6 +1051,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     post.steps[n++] = GemmStep{(short)kbh, 1, 32, COL_NET, 0, 0, 0};
     post.n_steps = n;
     pre.NV = post.NV = NV;
+    pre.NV_real = post.NV_real = s.NV;
     pre.spv = post.spv = ROWS / NV;
     pre.xc = post.xc = (float*)t.scratch;
     pre.out = post.out = q.out;

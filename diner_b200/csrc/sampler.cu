@@ -47,6 +47,9 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
     for (long long ray = (long long)blockIdx.x * WARPS_PER_CTA + warp; ray < total;
          ray += (long long)gridDim.x * WARPS_PER_CTA) {
         const int sb = (int)(ray / a.NR);
+        // counter-based fallback noise is keyed by the ray's LOGICAL index (scene, ray + ray_offset), so that a shard of a ray list
+        // (multi-GPU, chunked calls) draws what the whole list would draw; dense injected noise is indexed by the local ray
+        const long long rkey = ((long long)sb << 40) + (ray - (long long)sb * a.NR) + (long long)a.ray_offset;
         const float* r = a.rays + ray * 8;
         const float ox = r[0], oy = r[1], oz = r[2], dx = r[3], dy = r[4], dz = r[5];
         const float near = r[6], far = r[7];
@@ -59,7 +62,7 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
             if (i < C) {
                 float lin = (i < C / 2) ? __fmul_rn(a.lin_step, (float)i)
                                         : fmaf(-a.lin_step, (float)(C - 1 - i), a.lin_end);
-                float u = a.u_coarse ? a.u_coarse[ray * C + i] : rng_uniform(a.seed, 1, ray * C + i);
+                float u = a.u_coarse ? a.u_coarse[ray * C + i] : rng_uniform(a.seed, 1, rkey * C + i);
                 float sfrac = __fadd_rn(lin, __fmul_rn(u, a.cstep));
                 z = __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, sfrac)), __fmul_rn(far, sfrac));
             }
@@ -199,7 +202,7 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
         for (int g = lane; g < G; g += 32) {
             float val = 0.0f;
             if (any_nz) {
-                const float n = a.g_noise ? a.g_noise[ray * G + g] : rng_normal(a.seed, 2, ray * G + g);
+                const float n = a.g_noise ? a.g_noise[ray * G + g] : rng_normal(a.seed, 2, rkey * G + g);
                 val = __fadd_rn(__fmul_rn(n, sdev), mean);
             }
             buf0[NT + g] = val;
@@ -217,7 +220,7 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
             const float fstep = __fdiv_rn(__fsub_rn(far, near), (float)nmiss);
             for (int e = lane; e < K; e += 32) {
                 if (buf1[e] == 0.0f) {
-                    const float u = a.u_fill ? a.u_fill[ray * K + e] : rng_uniform(a.seed, 3, ray * K + e);
+                    const float u = a.u_fill ? a.u_fill[ray * K + e] : rng_uniform(a.seed, 3, rkey * K + e);
                     float z = __fadd_rn(near, __fmul_rn((float)e, fstep));
                     buf1[e] = __fadd_rn(z, __fmul_rn(u, fstep));
                 }

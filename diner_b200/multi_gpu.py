@@ -26,8 +26,9 @@ def render_sharded(render_fn, rays, group=None, packed=False, return_packed=Fals
 
     packed=False: render_fn(rays_shard) -> (rgb (SB,n,3), depth (SB,n)), e.g.
         ``lambda r: (lambda o: (o.fine.rgb, o.fine.depth))(renderer(model, r))``.
-    packed=True:  render_fn(rays_shard, out) writes (SB,n,4) = [r,g,b,depth] into the contiguous tensor `out`
-        (``lambda r, out: renderer.render_packed(model, r, out=out)``) -- the zero-copy path.
+    packed=True:  render_fn(rays_shard, out, ray_offset) writes (SB,n,4) = [r,g,b,depth] into the contiguous tensor `out`
+        (``lambda r, out, off: renderer.render_packed(model, r, out=out, ray_offset=off)``) -- the zero-copy path;
+        ray_offset = index of the shard's first ray, so that counter-based sampler noise does not depend on the world size.
     return_packed=True (with packed=True): returns the (SB,NR,4) image [r,g,b,depth] itself instead of the two views.
     """
     single = not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1
@@ -36,7 +37,7 @@ def render_sharded(render_fn, rays, group=None, packed=False, return_packed=Fals
         if not packed:
             return render_fn(rays)
         full = torch.empty(SB, NR, 4, device=rays.device, dtype=torch.float32)
-        render_fn(rays, full)
+        render_fn(rays, full, 0)
         return full if return_packed else (full[..., :3], full[..., 3])
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi, per = shard_bounds(NR, world, rank)
@@ -46,10 +47,10 @@ def render_sharded(render_fn, rays, group=None, packed=False, return_packed=Fals
     if n > 0:
         shard = rays[:, lo:hi] if SB == 1 else rays[:, lo:hi].contiguous()      # SB == 1: already contiguous
         if packed and (SB == 1 or n == per):
-            render_fn(shard, mine[:, :n] if n < per else mine)
+            render_fn(shard, mine[:, :n] if n < per else mine, lo)
         elif packed:
             tmp = torch.empty(SB, n, 4, device=rays.device, dtype=torch.float32)
-            render_fn(shard, tmp)
+            render_fn(shard, tmp, lo)
             mine[:, :n] = tmp
         else:
             rgb, depth = render_fn(shard.contiguous())

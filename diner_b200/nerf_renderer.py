@@ -76,11 +76,13 @@ class NeRFRendererDGS(torch.nn.Module):
         self.noise = None   # optional dict(u_coarse, g_noise, u_fill, seed): injected draws (tests) / seed
         self._calls = 0
 
-    def _noise_for_call(self):
+    def _noise_for_call(self, ray_offset=0):
+        """Injected dense noise / fixed seed when `self.noise` is set; else a fresh seed per call.  `ray_offset` = logical index
+        of the call's first ray (ray-sharded renders), see diner_noise.ray_offset."""
         if self.noise is not None:
-            return self.noise
+            return dict(self.noise, ray_offset=ray_offset) if ray_offset else self.noise
         self._calls += 1
-        return dict(seed=(torch.initial_seed() * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF)
+        return dict(seed=(torch.initial_seed() * 1000003 + self._calls) & 0xFFFFFFFFFFFFFFFF, ray_offset=ray_offset)
 
     @torch.no_grad()
     def sample_depthguided(self, rays, model, n_samples, n_candidates, depth_diff_max=0.05, n_gaussian=None):
@@ -118,12 +120,13 @@ class NeRFRendererDGS(torch.nn.Module):
         return DotMap(fine=self._format_outputs(w, rgb, depth, want_weights))
 
     @torch.no_grad()
-    def render_packed(self, model, rays, out=None):
+    def render_packed(self, model, rays, out=None, ray_offset=0):
         """forward() with the outputs packed as (SB,B,4) = [r,g,b,depth] (optionally written into `out`): what the ray-sharded
-        multi-GPU render all-gathers (diner_b200/multi_gpu.py)."""
+        multi-GPU render all-gathers (diner_b200/multi_gpu.py).  `ray_offset`: index of rays[:, 0] in the full ray list."""
         assert len(rays.shape) == 3
         return model.context().render_rgbd(rays.float().contiguous(), int(self.n_samples), int(self.n_depth_candidates),
-                                           int(self.n_gaussian), self.white_bkgd, model.mode_id(), self._noise_for_call(), out=out)
+                                           int(self.n_gaussian), self.white_bkgd, model.mode_id(),
+                                           self._noise_for_call(ray_offset), out=out)
 
     @torch.no_grad()
     def render_image(self, model, target_extrinsics, target_intrinsics, H, W, z_near, z_far):

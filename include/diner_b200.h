@@ -81,6 +81,8 @@ typedef struct diner_noise {
     const float* g_noise;
     const float* u_fill;
     uint64_t seed;
+    uint64_t ray_offset;   /* counter-based noise only: logical index (within its scene) of the call's first ray, so that a shard /
+                              chunk of a ray list draws the same noise as the whole list would (multi-GPU ray sharding) */
 } diner_noise;
 
 /* NeRFRendererDGS.forward (src/models/nerf_renderer.py:399-424): rays (SB,NR,8) = [o3,d3,near,far] ->

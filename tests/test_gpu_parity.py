@@ -203,6 +203,14 @@ def test_properties_and_edges():
         rend.noise = None
         empty = rend(model, rays[:, :0].contiguous())
         assert empty.fine.rgb.shape == (1, 0, 3)
+        # (4b) counter-based noise is keyed by the logical ray index: shards rendered with their ray_offset (what the multi-GPU
+        #      render does) reproduce the single-call image bit for bit, for any split
+        rend.noise = dict(seed=99)
+        whole = rend.render_packed(model, rays)
+        parts = [rend.render_packed(model, rays[:, lo:hi].contiguous(), ray_offset=lo) for lo, hi in ((0, 40), (40, 41), (41, 128))]
+        assert torch.equal(torch.cat(parts, 1), whole)
+        o = rend(model, rays)
+        assert torch.equal(whole[..., :3], o.fine.rgb) and torch.equal(whole[..., 3], o.fine.depth)
     # (5) loud failures instead of fallbacks
     with pytest.raises(RuntimeError):
         model.context().render(rays.cpu(), 32, 200, 12, True, 0)
@@ -361,7 +369,8 @@ def test_other_config_shapes_forward(name, cfg):
 
 
 @pytest.mark.parametrize("NV,SB,K,nr", [(1, 1, 8, 1), (1, 2, 16, 37), (2, 1, 40, 300), (4, 1, 64, 1000), (4, 2, 24, 2500),
-                                        (8, 1, 16, 1200), (8, 1, 64, 3000), (2, 2, 64, 4100), (4, 1, 128, 4096)])
+                                        (8, 1, 16, 1200), (8, 1, 64, 3000), (2, 2, 64, 4100), (4, 1, 128, 4096),
+                                        (3, 1, 20, 700), (6, 2, 16, 900)])      # view counts that are not powers of two: padded rows
 def test_pair_kernel_pipeline_shape_sweep(NV, SB, K, nr):
     """The software pipeline of the CTA-pair kernel (per-K-block release barriers, cross-tile hand-off, helper warps)
     over many tile counts -- 1 tile to >10 rounds per CTA, live and padded last rounds, 1..8 views: parity mode must agree
@@ -594,3 +603,31 @@ def test_encode_path_borrows_channels_last_latent():
         c = rend(model, rays.cuda())
     assert torch.equal(a.fine.rgb, c.fine.rgb) and torch.equal(a.fine.depth, c.fine.depth)
     assert bool(torch.isfinite(a.fine.rgb).all()) and float(a.fine.rgb.std()) > 0
+
+
+def test_cam_sweep_loop_and_output_side(tmp_path):
+    """Callers around the hot path: the camera-sweep render loop (diner.py:180-211) and the output side (torch_cmap + image
+    files, diner.py:120-133) on the device."""
+    from diner_b200 import io as IO
+    from diner_b200.predict import cam_sweep_frames, predict_imgs_from_batch, save_sweep
+    cfg = dict(H=32, W=48, NV=4, SB=1, near=1.0, far=2.5, K=16, C=100, G=6, white=True, nr=8, seed=17)
+    batch, latent, mlp, _, _ = MG.case_inputs(cfg)
+    model = product_model(batch, latent, mlp, "cuda", "parity")
+    rend = renderer_for(cfg)
+    rend.noise = dict(seed=11)
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    b["target_rgb"] = torch.zeros(1, 3, cfg["H"], cfg["W"], device="cuda")
+    ext = b["target_extrinsics"].repeat(3, 1, 1)
+    ext[1, 0, 3] += 0.05
+    ext[2, 0, 3] += 0.10
+    frames = cam_sweep_frames(model, rend, b, ext, cfg["near"], cfg["far"], encode=False)
+    assert frames.shape == (5, 3, 2 * cfg["H"], cfg["W"]) and torch.equal(frames[0], frames[4]) and torch.equal(frames[1], frames[3])
+    assert not torch.equal(frames[0], frames[2]) and bool(torch.isfinite(frames).all())
+    rgb, depth = predict_imgs_from_batch(model, rend, b, cfg["near"], cfg["far"], return_depth=True, encode=False)
+    assert torch.equal(rgb[0], frames[0][:, :cfg["H"]])                     # same seed -> the sweep's first frame is the plain prediction
+    assert torch.equal(IO.torch_cmap(depth)[0].float(), frames[0][:, cfg["H"]:])
+    files = save_sweep(frames, str(tmp_path / "sweep.mp4"))
+    assert files and all(os.path.exists(f) for f in files)
+    w = IO.ImageWriter()
+    IO.write_prediction_images(w, str(tmp_path), ["s0"], rgb, depth, b["src_rgbs"], b["target_rgb"])
+    assert len(w.close()) == 4

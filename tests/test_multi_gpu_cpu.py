@@ -27,7 +27,7 @@ def _worker(rank, world, port, n_rays, q):
     ref_rgb, ref_depth = _fake_render(rays)
     ok = bool(torch.equal(rgb, ref_rgb) and torch.equal(depth, ref_depth))
 
-    def packed(r, out):                                   # the zero-copy contract: write (SB,n,4) into the gather slice
+    def packed(r, out, ray_offset):                       # the zero-copy contract: write (SB,n,4) into the gather slice
         c, d = _fake_render(r)
         out[..., :3] = c
         out[..., 3] = d
