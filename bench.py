@@ -393,14 +393,16 @@ def main():
         pk = peaks()
         rays_per_s = n_total * args.steps / (ms * 1e-3)
         n_samp_rank = (hi - lo) * K
-        n_pre_launches = -(-n_samp_rank // 524288)
+        fused = stage["mlp_post"] == 0.0                # FUSED launch: one kernel runs the per sample-view AND the per sample layers
+        n_pre_launches = 1 if fused else -(-n_samp_rank // 524288)
         pre_ms_per_launch = stage["mlp_pre"] / n_pre_launches if stage["mlp_pre"] > 0 else None
-        pre_flops_per_launch = FLOP_PRE_PER_SAMPLE * n_samp_rank / n_pre_launches
+        pre_flops_per_launch = (FLOP_PER_SAMPLE if fused else FLOP_PRE_PER_SAMPLE) * n_samp_rank / n_pre_launches
         achieved = pre_flops_per_launch / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
-        # FLOPs the PRE kernel actually issues to the tensor pipe per sample-view: lin_in + 3 x (fc_0 + fc_1) (lin_z is hoisted
-        # into the once-per-scene Y maps), x3 MMAs per product in parity mode
-        exec_per_sv = (2 * 64 * 512 + 6 * 2 * 512 * 512) * (3 if args.mode == "parity" else 1)
-        executed = exec_per_sv * NV * n_samp_rank / n_pre_launches / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
+        # FLOPs the kernel actually issues to the tensor pipe per sample: NV x (lin_in + 3 x (fc_0 + fc_1)) (lin_z is hoisted into
+        # the once-per-scene Y maps) [+ 2 x (fc_0 + fc_1) + lin_out (N = 32) in the fused kernel], x3 MMAs per product in parity mode
+        passes = 3 if args.mode == "parity" else 1
+        exec_per_sample = NV * (2 * 64 * 512 + 6 * 2 * 512 * 512) + (4 * 2 * 512 * 512 + 2 * 512 * 32 if fused else 0)
+        executed = passes * exec_per_sample * n_samp_rank / n_pre_launches / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
         tr = latest_traffic() if args.mode == "parity" else None
         e2e_d2h = (rgb_h.numel() + dep_h.numel()) * 4 if world == 1 else img_h.numel() * 4
         line = {
@@ -412,15 +414,18 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD},
             "run": {"mode": args.mode, "rays_per_step": n_total, "sharding": "rays/%d" % world,
-                    "l2": "inputs larger than L2 (%.1f GB fp32 lin_z maps gathered per sample-view, 1 GiB activations scratch per 524288 samples)"
-                          % (3 * NV * ((H + 128) // 2) * ((W + 128) // 2) * 512 * 4 / 1e9),
+                    "l2": "inputs larger than L2 (%.1f GB fp32 lin_z maps gathered per sample-view, %.0f MB of sample depths + per-sample outputs per step)"
+                          % (3 * NV * ((H + 128) // 2) * ((W + 128) // 2) * 512 * 4 / 1e9, n_total * K * 20 / 1e6),
                     "tail_kb": int(os.environ.get("DINER_TC_TAIL_KB", "-1")),
                     "e2e_path": "diner_render_host (C ABI, host buffers)" if world == 1 else "pinned host rays -> sharded render + all-gather -> host image"},
             "e2e": {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                     "h2d_bytes_per_step": rays_host.numel() * 4, "d2h_bytes_per_step": e2e_d2h},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "tc2::mlp_pair_kernel<PRE> (per sample-view ResnetFC layers; algorithmic FLOPs per SURVEY 8(d), incl. the hoisted lin_z)",
+            "roofline": {"bound": "tensor", "kernel": ("tc2::mlp_pair_kernel<FUSED> (the whole ResnetFC: per sample-view layers, view combine, per sample layers; "
+                                                       "algorithmic FLOPs per SURVEY 8(d) = 21.2 MFLOP per sample, incl. the hoisted lin_z)") if fused else
+                                                      "tc2::mlp_pair_kernel<PRE> (per sample-view ResnetFC layers; algorithmic FLOPs per SURVEY 8(d), incl. the hoisted lin_z)",
+                         "launches_per_step": n_pre_launches,
                          "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["sustained"], "peak_source": pk["src"] + " bf16 dense sustained (fp16 runs at the same rate)",
                          "achieved_executed_mma": executed,

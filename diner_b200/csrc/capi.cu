@@ -500,7 +500,10 @@ extern "C" int diner_render_host(diner_ctx* c, const float* rays_host, int SB, i
 
 extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) {
     if (!c || !key) return fail(DINER_E_INVALID, "NULL ctx / key");
-    if (!strcmp(key, "tail_kb")) {
+    if (!strcmp(key, "fused")) {
+        if (value != 0 && value != 1) return fail(DINER_E_INVALID, "fused must be 0 or 1");
+        c->tc.fused = (int)value;
+    } else if (!strcmp(key, "tail_kb")) {
         if (value < 0 || value > 4) return fail(DINER_E_INVALID, "tail_kb must be in [0,4]");
         c->tc.tail_kb = (int)value;
     } else if (!strcmp(key, "early_split")) {

@@ -100,7 +100,8 @@ struct GemmStep {
     short n_width;     // UMMA N: 256, or 32 for lin_out
     short dst_col;     // TMEM column base
     short accumulate;
-    short release;     // commit the per-K-block "A operand free" barriers (a gather into A overlaps / follows the step); 2 = lin_in
+    short release;     // commit the per-K-block "A operand free" barriers (a gather into A overlaps / follows the step); 2 = lin_in;
+                       // 3 = fc_1 of the last PRE block: only when another PRE tile follows (its early gather consumes the phases)
     short tail;        // the last `tail` K blocks are issued N-tile-outer (accumulator N tile 0 completes early -> bar_acc0)
 };
 
@@ -115,6 +116,12 @@ struct Args {
     const float* bias2;         // pair-kernel PRE rows: [0,n_pre) bias folded into Y_b, row n_pre = b_fc1[n_pre-1] (added at the combine)
     GemmStep steps[MAX_STEPS];
     int n_steps, n_blocks, uses_per_tile;
+    // FUSED launch: a round = ppr PRE tiles (ppr * spv = 64 samples) followed by ONE POST tile over the same 64 samples; the view-combined
+    // activations x_c go through a per-CTA slab of `xc` (64 x 512 fp32 = 128 KiB, L2 resident) instead of a sub-batch sized HBM scratch
+    GemmStep steps_post[2 * DINER_MAX_BLOCKS + 1];
+    int n_steps_post, n_blocks_post, uses_post, ppr;
+    const int* tile_table_post;
+    const float* bias_post;
     long long s_begin, n_samples, n_total, n_tiles;   // n_tiles counts 64-row CTA tiles
     int NV, spv;                // NV = views per sample padded to a power of two (rows of a sample are NV adjacent rows), spv = 64 / NV
     int NV_real;                // the scene's view count: rows of the padding views repeat view 0 and are masked out of the combine
@@ -494,11 +501,11 @@ __device__ __forceinline__ void opnd_warps_join() {
 #define TS(role, slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && lane == 0) a.dbg_ts[(blockIdx.x * 4 + (role)) * 64 + (slot)] = clock64(); } while (0)
 #define TSW() do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && wwarp == 0 && lane == 0 && tsn < 64) a.dbg_ts[(blockIdx.x * 4 + 1) * 64 + tsn++] = clock64(); } while (0)
 // ---- the kernel ----------------------------------------------------------------------------------
-constexpr int KIND_PRE = 0, KIND_POST = 1, KIND_ZMAP = 2;
+constexpr int KIND_PRE = 0, KIND_POST = 1, KIND_ZMAP = 2, KIND_FUSED = 3;
 template <bool PARITY, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_pair_kernel(const __grid_constant__ Args a) {
     using C = Cfg<PARITY>;
-    constexpr bool POST = KIND == KIND_POST;
+    constexpr bool FUSED = KIND == KIND_FUSED;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
@@ -539,7 +546,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     // both CTAs of a pair run the same number of rounds; CTA tile = 2 * pair_tile + rank
     const long long first = (long long)blockIdx.x, stride = (long long)gridDim.x;
     const long long n_rounds = (a.n_tiles + stride - 1) / stride;
-    const long long total_uses = n_rounds * a.uses_per_tile;
+    const int uses_per_round = FUSED ? a.ppr * a.uses_per_tile + a.uses_post : a.uses_per_tile;
+    const long long total_uses = n_rounds * uses_per_round;
 
     const int prod_idx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
     if (prod_idx >= 0) {
@@ -547,16 +555,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         //       2-SM TMA: both CTAs' copies complete_tx on the LEADER's full barrier, so the MMA issuer needs no software relay.
         const bool leader = elect_one();
         const int* table = a.tile_table + (size_t)crank * a.uses_per_tile;
+        const int* table_post = FUSED ? a.tile_table_post + (size_t)crank * a.uses_post : nullptr;
         const uint32_t leader_full = map_to_cta(bar_full, 0);
         for (long long base = 0; base < total_uses; base += C::NST) {
             for (int st = prod_idx; st < C::NST; st += NUM_PRODUCERS) {
                 const long long use = base + st;
                 if (use >= total_uses) break;
-                const int t = (int)(use % a.uses_per_tile);
+                const int t = (int)(use % uses_per_round);
                 const uint32_t ph = (uint32_t)((use / C::NST) & 1);
                 mbar_wait(bar_empty + 8 * st, ph ^ 1, a.err, 10);
                 if (leader) {
-                    const int tix = __ldg(table + t);
+                    const int tix = (!FUSED || t < a.ppr * a.uses_per_tile) ? __ldg(table + t % a.uses_per_tile)
+                                                                            : __ldg(table_post + (t - a.ppr * a.uses_per_tile));
                     const bool small = (tix & TILE_SMALL) != 0;          // lin_out: only the first 16 rows of the tile are read
                     const int row = (tix & (TILE_SMALL - 1)) * 128;
                     if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, small ? 2 * SMALL_TILE_BYTES : 2 * WTILE_BYTES);
@@ -572,9 +582,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         //       released (bar_afree) right after its last MMA when the step is followed by a gather into the operand buffers.
         const bool leader = elect_one();
         uint32_t use = 0, oph[2] = {0, 0};
-        for (long long rd = 0; rd < n_rounds; ++rd) {
-            for (int sidx = 0; sidx < a.n_steps; ++sidx) {
-                const GemmStep gs = a.steps[sidx];
+        // the GEMM steps of one tile; cold = no previous PRE tile prepared this one (the whole Y_0 gather follows lin_in),
+        // has_next = another PRE tile follows in the pipeline (its early gather consumes the last fc_1's operand releases)
+        auto run_steps = [&](const GemmStep* steps, int n_steps, bool cold, bool has_next, long long rd) {
+            for (int sidx = 0; sidx < n_steps; ++sidx) {
+                GemmStep gs = steps[sidx];
+                if (gs.release == 3) gs.release = has_next ? 1 : 0;
                 const uint32_t idesc = make_idesc2(gs.n_width);
                 // K blocks [0, kb_split) K-block-outer over both N tiles; the tail [kb_split, nkb) N-tile-outer: N tile 0 of the
                 // accumulator completes `tail` K blocks early (bar_acc0) and its epilogue half overlaps the n1 tail
@@ -642,11 +655,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 if (leader) {
                     // lin_in (release == 2) reads K block 0 only; in the first round the gather of the whole Y_0 row set follows it, so
                     // the other K blocks are released here as well (later rounds gather them during the previous tile's last fc_1)
-                    if (gs.release == 2 && rd == 0) for (int kb = gs.nkb; kb < HID / KBLK; ++kb) umma2_commit_pair(bar_afree + 8 * kb);
+                    if (gs.release == 2 && cold) for (int kb = gs.nkb; kb < HID / KBLK; ++kb) umma2_commit_pair(bar_afree + 8 * kb);
                     umma2_commit_pair(bar_acc);
                 }
                 __syncwarp();
                 TS(0, 4 * sidx + 2);
+            }
+        };
+        for (long long rd = 0; rd < n_rounds; ++rd) {
+            if constexpr (FUSED) {
+                for (int j = 0; j < a.ppr; ++j) run_steps(a.steps, a.n_steps, j == 0, j + 1 < a.ppr, rd * a.ppr + j);
+                run_steps(a.steps_post, a.n_steps_post, false, false, -1);
+            } else {
+                run_steps(a.steps, a.n_steps, rd == 0, rd + 1 < n_rounds, rd);
             }
         }
     } else if (warp >= WORKER_WARP0) {
@@ -658,8 +679,205 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const int r = 32 * (q & 1) + lane;
         uint32_t it = 0, ph0 = 0, ph1 = 0;   // phase counters: bar_acc, bar_afree[0], bar_afree[1..7]
         (void)ph0; (void)ph1;
-        for (long long rd = 0; rd < n_rounds; ++rd) {
+        // One PRE tile (64 sample-view rows).  cold: nothing was prepared by a previous tile; has_next: tile_next follows in the
+        // pipeline (its taps / features / Y_0 are produced under this tile's last block); pt: running PRE tile count (tap buffer
+        // parity); xc_row0 (FUSED): first row of this tile's samples in the CTA's x_c slab.
+        auto pre_tile = [&](long long tile, bool live, bool cold, bool has_next, long long tile_next, long long pt, long long xc_row0) {
+            // Tile pipeline (steady state, !cold): the taps and the lin_in features of this tile, and the Y_0 staging of
+            // K blocks 1..7, were produced during the previous tile's last block; its lin_in was handed off after that tile's combine.
             int tsn = 0; (void)tsn;
+            const long long rd = pt; (void)rd;
+            const Tap* tp = taps + (pt & 1) * ROWS;
+            Tap* tn = taps + ((pt + 1) & 1) * ROWS;
+            if (cold) {
+                prep_rows<PARITY, NUM_OPND_WARPS * 32 / 64, true, true>(a, tile, wt, Ahi, Alo, taps);
+                opnd_warps_join();
+                if (!helper) worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                   // -> lin_in (K block 0 only)
+            }
+            TSW();
+            for (int b = 0; b < a.n_blocks; ++b) {
+                const bool last = b + 1 == a.n_blocks;
+                // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gathered into the operand buffers K block by K block while the
+                // previous GEMM (lin_in / fc_1[b-1]) is still running, then added to the residual in the epilogue
+                if (b == 0 && !cold) {       // only K block 0 is left (it held the lin_in features until now)
+                    gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tp, 0, 0, bar_afree, ph0 & 1, ph1 & 1); ++ph0;
+                } else {
+                    gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, tp, 0, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.worker_kb_hi);
+                    ++ph0; ++ph1;
+                }
+                TSW();
+                // Helpers never wait on bar_acc in this kernel: they are gated by bar_afree alone.  (A helper that finishes a late
+                // gather could reach a bar_acc wait after the barrier has already completed its NEXT phase -- lin_in of the next
+                // tile is short -- and a parity wait that is one phase late blocks for good.)
+                if (!helper) mbar_wait(bar_acc0, it & 1, a.err, 40);                                               // x, N tile 0 (hidden 0..255) complete
+                TSW();
+                tc_fence_after();
+                if (helper) {
+                    asm volatile("bar.arrive 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                        // staging of K blocks 5..7 complete
+                    if (last && has_next) {  // taps of the next tile, while fc_0 of the last block runs
+                        if (wt - NUM_WORKERS < ROWS) prep_rows<PARITY, 1, true, false>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                        asm volatile("bar.sync 9, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");                    // all helpers read these taps below
+                        asm volatile("bar.arrive 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                    }
+                } else {
+                    asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..4 complete
+                    if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 0);
+                    TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 0..3
+                    asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                    mbar_wait(bar_acc, it & 1, a.err, 41); ++it;                                                    // x complete
+                    tc_fence_after();
+                    if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 1);
+                    TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 4..7
+                }
+                if (!helper) {
+                    mbar_wait(bar_acc0, it & 1, a.err, 42); TSW();                                                  // net, N tile 0
+                    tc_fence_after();
+                    const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
+                    if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
+                    TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 0..3
+                    mbar_wait(bar_acc, it & 1, a.err, 39); ++it;                                                    // net complete
+                    tc_fence_after();
+                    if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
+                    TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 4..7
+                }
+                if (last && has_next) {
+                    // next tile, under the last fc_1: lin_in features into K block 0 as soon as fc_1 has consumed it (helpers),
+                    // Y_0 staging of K blocks 1..7 as they are released (everyone)
+                    if (helper) {
+                        mbar_wait(bar_afree, ph0 & 1, a.err, 47);
+                        prep_rows<PARITY, NUM_HELPER_WARPS * 32 / 64, false, true>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                        fence_proxy_async();
+                        asm volatile("bar.arrive 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                    // features in place
+                    } else {
+                        asm volatile("bar.sync 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                      // next taps in place
+                    }
+                    gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.early_worker_kb_hi);
+                    // workers consume K block 0's phase too (the helpers did above -- and must NOT wait on it again here: by the time
+                    // they finish their late K blocks, lin_in of the next tile may already have completed the barrier's next phase)
+                    if (!helper) mbar_wait(bar_afree, ph0 & 1, a.err, 48);
+                    ++ph0; ++ph1;
+                }
+            }
+            // last fc_1: a worker warp combines only its own N tile of x, so the n2 == 0 warps start on bar_acc0.  They skip
+            // this phase of bar_acc, which is safe: their next wait on it follows a wait on the NEXT phase of bar_acc0, and the
+            // commits of one issuer complete in order
+            const uint32_t it_last = it;
+            if (!helper) {
+                mbar_wait(bar_acc0, it & 1, a.err, 43);
+                if (n2 == 1) mbar_wait(bar_acc, it & 1, a.err, 38);
+                ++it;
+            }
+            TSW();
+            tc_fence_after();
+            // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
+            const float* cb = a.bias2 + (size_t)a.n_blocks * HID;                // b_fc1 of the last block (everything earlier is in x already)
+            // destination row of this row's sample: its index in the sub-batch (PRE launch) or in this CTA's slab (FUSED)
+            const long long smp = tile * a.spv + r / a.NV;
+            const bool wr = FUSED || (live && smp < a.n_samples);
+            float* dst_sample = a.xc + (size_t)(FUSED ? xc_row0 + r / a.NV : (wr ? smp : 0)) * HID;
+#pragma unroll 1
+            for (int c32 = 0; c32 < ((helper || (a.dbg_skip & 128)) ? 0 : 4); ++c32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
+                const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
+                switch (a.NV) {
+                    case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                    case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                    case 4: combine_store<4>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                    case 8: combine_store<8>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                    case 16: combine_store<16>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                    default: combine_store<32>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                }
+            }
+            tc_fence_before();
+            if (has_next && !helper) {
+                asm volatile("bar.sync 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // next tile's features in place
+                worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // X read out -> lin_in of the next tile
+            }
+            if (FUSED && !has_next && !helper) {
+                // the POST tile overwrites TMEM X and the whole A operand: the last fc_1 must be complete (the n2 == 0 warps only
+                // waited for its N tile 0 above), every worker done reading X, and the x_c slab rows visible to the whole CTA
+                if (n2 == 0) mbar_wait(bar_acc, it_last & 1, a.err, 37);
+                __threadfence_block();
+                asm volatile("bar.sync 10, %0;" ::"n"(NUM_WORKERS) : "memory");
+            }
+        };
+        // One POST tile (64 samples): remaining blocks + lin_out on the view-combined activations.
+        auto post_tile = [&](long long tile, bool live, const float* bias, int n_blocks, long long xc_row0) {
+            // load x_c: W_SCALE * x_c -> TMEM X (the residual the fc_1 steps accumulate onto), relu(x_c) -> A operand
+            long long smp = FUSED ? xc_row0 + r : tile * ROWS + r;          // row of the CTA's slab (FUSED) / sample of the sub-batch
+            if (!FUSED && smp >= a.n_samples) smp = a.n_samples - 1;
+#pragma unroll 1
+            for (int c32 = 0; c32 < (helper ? 0 : 4); ++c32) {
+                const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
+                const float4* src = (const float4*)(a.xc + (size_t)smp * HID + h0);
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 f = FUSED ? __ldcg(src + i) : __ldg(src + i);     // FUSED: written by this kernel -> no read-only path
+                    v[4 * i] = __float_as_uint(f.x * W_SCALE); v[4 * i + 1] = __float_as_uint(f.y * W_SCALE);
+                    v[4 * i + 2] = __float_as_uint(f.z * W_SCALE); v[4 * i + 3] = __float_as_uint(f.w * W_SCALE);
+                }
+                tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[8 * c8 + i]), 0.0f) * W_INV;
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    const uint32_t off = act_off(r, (h0 >> 3) + c8);
+                    *(uint4*)(Ahi + off) = hi;
+                    if (PARITY) *(uint4*)(Alo + off) = lo;
+                }
+            }
+            if (!helper) {                                                                                          // -> fc_0 of the first post block
+                worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+            }
+            for (int b = 0; b < n_blocks; ++b) {
+                if (!helper) {
+                    const float* b0 = bias + (size_t)(n_blocks + 1 + b) * HID;
+                    mbar_wait(bar_acc0, it & 1, a.err, 50);                                                         // net, N tile 0
+                    tc_fence_after();
+                    epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
+                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b], K blocks 0..3
+                    mbar_wait(bar_acc, it & 1, a.err, 53); ++it;
+                    tc_fence_after();
+                    epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
+                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    const float* b1 = bias + (size_t)(b + 1) * HID;
+                    mbar_wait(bar_acc0, it & 1, a.err, 51);                                                         // x, N tile 0
+                    tc_fence_after();
+                    epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
+                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> next fc_0 / lin_out
+                    mbar_wait(bar_acc, it & 1, a.err, 54); ++it;
+                    tc_fence_after();
+                    epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
+                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                }
+            }
+            if (!helper) {                                                   // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
+                mbar_wait(bar_acc0, it & 1, a.err, 55);
+                mbar_wait(bar_acc, it & 1, a.err, 52); ++it;
+            }
+            tc_fence_after();
+            if (!helper && q < 2 && n2 == 0) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)COL_NET, v);
+                const long long s_loc = tile * ROWS + r;
+                if (live && s_loc < a.n_samples) {
+                    const float4 bo = __ldg((const float4*)(bias + (size_t)(2 * n_blocks + 1) * HID));
+                    const float x0 = fmaf(__uint_as_float(v[0]), W_INV, bo.x), x1 = fmaf(__uint_as_float(v[1]), W_INV, bo.y);
+                    const float x2 = fmaf(__uint_as_float(v[2]), W_INV, bo.z), x3 = fmaf(__uint_as_float(v[3]), W_INV, bo.w);
+                    ((float4*)a.out)[a.s_begin + s_loc] = make_float4(1.0f / (1.0f + expf(-x0)), 1.0f / (1.0f + expf(-x1)),
+                                                                     1.0f / (1.0f + expf(-x2)), fmaxf(x3, 0.0f));
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+        };
+        for (long long rd = 0; rd < n_rounds; ++rd) {
             const long long tile_raw = first + rd * stride;
             const bool live = tile_raw < a.n_tiles;
             const long long tile = live ? tile_raw : a.n_tiles - 1;
@@ -686,190 +904,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         }
                     }
                 }
-            } else if constexpr (!POST) {
-                // Tile pipeline (steady state, round rd > 0): the taps and the lin_in features of this tile, and the Y_0 staging of
-                // K blocks 1..7, were produced during the previous tile's last block; lin_in(rd) was handed off after its combine.
-                const Tap* tp = taps + (rd & 1) * ROWS;
-                Tap* tn = taps + ((rd + 1) & 1) * ROWS;
-                const bool has_next = rd + 1 < n_rounds;
+            } else if constexpr (KIND == KIND_PRE) {
                 long long tile_next = first + (rd + 1) * stride;
                 if (tile_next >= a.n_tiles) tile_next = a.n_tiles - 1;
-                if (rd == 0) {
-                    prep_rows<PARITY, NUM_OPND_WARPS * 32 / 64, true, true>(a, tile, wt, Ahi, Alo, taps);
-                    opnd_warps_join();
-                    if (!helper) worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                   // -> lin_in (K block 0 only)
-                }
-                TSW();
-                for (int b = 0; b < a.n_blocks; ++b) {
-                    const bool last = b + 1 == a.n_blocks;
-                    // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gathered into the operand buffers K block by K block while the
-                    // previous GEMM (lin_in / fc_1[b-1]) is still running, then added to the residual in the epilogue
-                    if (b == 0 && rd > 0) {      // only K block 0 is left (it held the lin_in features until now)
-                        gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tp, 0, 0, bar_afree, ph0 & 1, ph1 & 1); ++ph0;
-                    } else {
-                        gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, tp, 0, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.worker_kb_hi);
-                        ++ph0; ++ph1;
-                    }
-                    TSW();
-                    // Helpers never wait on bar_acc in this kernel: they are gated by bar_afree alone.  (A helper that finishes a late
-                    // gather could reach a bar_acc wait after the barrier has already completed its NEXT phase -- lin_in of the next
-                    // tile is short -- and a parity wait that is one phase late blocks for good.)
-                    if (!helper) mbar_wait(bar_acc0, it & 1, a.err, 40);                                               // x, N tile 0 (hidden 0..255) complete
-                    TSW();
-                    tc_fence_after();
-                    if (helper) {
-                        asm volatile("bar.arrive 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                        // staging of K blocks 5..7 complete
-                        if (last && has_next) {  // taps of the next tile, while fc_0 of the last block runs
-                            if (wt - NUM_WORKERS < ROWS) prep_rows<PARITY, 1, true, false>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
-                            asm volatile("bar.sync 9, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");                    // all helpers read these taps below
-                            asm volatile("bar.arrive 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
-                        }
-                    } else {
-                        asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..4 complete
-                        if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 0);
-                        TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 0..3
-                        asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
-                        mbar_wait(bar_acc, it & 1, a.err, 41); ++it;                                                    // x complete
-                        tc_fence_after();
-                        if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 1);
-                        TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 4..7
-                    }
-                    if (!helper) {
-                        mbar_wait(bar_acc0, it & 1, a.err, 42); TSW();                                                  // net, N tile 0
-                        tc_fence_after();
-                        const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
-                        if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
-                        TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 0..3
-                        mbar_wait(bar_acc, it & 1, a.err, 39); ++it;                                                    // net complete
-                        tc_fence_after();
-                        if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
-                        TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 4..7
-                    }
-                    if (last && has_next) {
-                        // next tile, under the last fc_1: lin_in features into K block 0 as soon as fc_1 has consumed it (helpers),
-                        // Y_0 staging of K blocks 1..7 as they are released (everyone)
-                        if (helper) {
-                            mbar_wait(bar_afree, ph0 & 1, a.err, 47);
-                            prep_rows<PARITY, NUM_HELPER_WARPS * 32 / 64, false, true>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
-                            fence_proxy_async();
-                            asm volatile("bar.arrive 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                    // features in place
-                        } else {
-                            asm volatile("bar.sync 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                      // next taps in place
-                        }
-                        gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.early_worker_kb_hi);
-                        // workers consume K block 0's phase too (the helpers did above -- and must NOT wait on it again here: by the time
-                        // they finish their late K blocks, lin_in of the next tile may already have completed the barrier's next phase)
-                        if (!helper) mbar_wait(bar_afree, ph0 & 1, a.err, 48);
-                        ++ph0; ++ph1;
-                    }
-                }
-                // last fc_1: a worker warp combines only its own N tile of x, so the n2 == 0 warps start on bar_acc0.  They skip
-                // this phase of bar_acc, which is safe: their next wait on it follows a wait on the NEXT phase of bar_acc0, and the
-                // commits of one issuer complete in order
-                if (!helper) {
-                    mbar_wait(bar_acc0, it & 1, a.err, 43);
-                    if (n2 == 1) mbar_wait(bar_acc, it & 1, a.err, 38);
-                    ++it;
-                }
-                TSW();
-                tc_fence_after();
-                // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
-                const float* cb = a.bias2 + (size_t)a.n_blocks * HID;                // b_fc1 of the last block (everything earlier is in x already)
-                const long long smp = tile * a.spv + r / a.NV;                   // sample within the sub-batch
-                const bool wr = live && smp < a.n_samples;
-                float* dst_sample = a.xc + (size_t)(wr ? smp : 0) * HID;
-#pragma unroll 1
-                for (int c32 = 0; c32 < ((helper || (a.dbg_skip & 128)) ? 0 : 4); ++c32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
-                    const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
-                    switch (a.NV) {
-                        case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                        case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                        case 4: combine_store<4>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                        case 8: combine_store<8>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                        case 16: combine_store<16>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                        default: combine_store<32>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                    }
-                }
-                tc_fence_before();
-                if (has_next && !helper) {
-                    asm volatile("bar.sync 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // next tile's features in place
-                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // X read out -> lin_in of the next tile
-                }
+                pre_tile(tile, live, rd == 0, rd + 1 < n_rounds, tile_next, rd, 0);
+            } else if constexpr (KIND == KIND_POST) {
+                post_tile(tile, live, a.bias, a.n_blocks, 0);
             } else {
-                // load x_c: W_SCALE * x_c -> TMEM X (the residual the fc_1 steps accumulate onto), relu(x_c) -> A operand
-                long long smp = tile * ROWS + r;
-                if (smp >= a.n_samples) smp = a.n_samples - 1;
-#pragma unroll 1
-                for (int c32 = 0; c32 < (helper ? 0 : 4); ++c32) {
-                    const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
-                    const float4* src = (const float4*)(a.xc + (size_t)smp * HID + h0);
-                    uint32_t v[32];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 f = __ldg(src + i);
-                        v[4 * i] = __float_as_uint(f.x * W_SCALE); v[4 * i + 1] = __float_as_uint(f.y * W_SCALE);
-                        v[4 * i + 2] = __float_as_uint(f.z * W_SCALE); v[4 * i + 3] = __float_as_uint(f.w * W_SCALE);
-                    }
-                    tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        float x[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[8 * c8 + i]), 0.0f) * W_INV;
-                        uint4 hi, lo;
-                        split8(x, hi, lo);
-                        const uint32_t off = act_off(r, (h0 >> 3) + c8);
-                        *(uint4*)(Ahi + off) = hi;
-                        if (PARITY) *(uint4*)(Alo + off) = lo;
-                    }
-                }
-                if (!helper) {                                                                                          // -> fc_0 of the first post block
-                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                }
-                for (int b = 0; b < a.n_blocks; ++b) {
-                    if (!helper) {
-                        const float* b0 = a.bias + (size_t)(a.n_blocks + 1 + b) * HID;
-                        mbar_wait(bar_acc0, it & 1, a.err, 50);                                                         // net, N tile 0
-                        tc_fence_after();
-                        epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
-                        worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> fc_1[b], K blocks 0..3
-                        mbar_wait(bar_acc, it & 1, a.err, 53); ++it;
-                        tc_fence_after();
-                        epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
-                        worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                        const float* b1 = a.bias + (size_t)(b + 1) * HID;
-                        mbar_wait(bar_acc0, it & 1, a.err, 51);                                                         // x, N tile 0
-                        tc_fence_after();
-                        epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
-                        worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> next fc_0 / lin_out
-                        mbar_wait(bar_acc, it & 1, a.err, 54); ++it;
-                        tc_fence_after();
-                        epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
-                        worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                    }
-                }
-                if (!helper) {                                                   // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
-                    mbar_wait(bar_acc0, it & 1, a.err, 55);
-                    mbar_wait(bar_acc, it & 1, a.err, 52); ++it;
-                }
-                tc_fence_after();
-                if (!helper && q < 2 && n2 == 0) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)COL_NET, v);
-                    const long long s_loc = tile * ROWS + r;
-                    if (live && s_loc < a.n_samples) {
-                        const float4 bo = __ldg((const float4*)(a.bias + (size_t)(2 * a.n_blocks + 1) * HID));
-                        const float x0 = fmaf(__uint_as_float(v[0]), W_INV, bo.x), x1 = fmaf(__uint_as_float(v[1]), W_INV, bo.y);
-                        const float x2 = fmaf(__uint_as_float(v[2]), W_INV, bo.z), x3 = fmaf(__uint_as_float(v[3]), W_INV, bo.w);
-                        ((float4*)a.out)[a.s_begin + s_loc] = make_float4(1.0f / (1.0f + expf(-x0)), 1.0f / (1.0f + expf(-x1)),
-                                                                         1.0f / (1.0f + expf(-x2)), fmaxf(x3, 0.0f));
-                    }
-                }
-                tc_fence_before();
-                asm volatile("bar.sync 1, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                // FUSED: a.n_tiles counts 64-sample rounds; PRE tile j covers samples [64 * tile + j * spv, + spv)
+                const long long slab = (long long)blockIdx.x * ROWS;
+                for (int j = 0; j < a.ppr; ++j)
+                    pre_tile(tile * a.ppr + j, live, j == 0, j + 1 < a.ppr, tile * a.ppr + j + 1, rd * a.ppr + j, slab + (long long)j * a.spv);
+                post_tile(tile, live, a.bias_post, a.n_blocks_post, slab);
             }
         }
     }
@@ -1017,7 +1063,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     if (t.timing && !t.ev[0]) for (int i = 0; i < 4; ++i) TCK(cudaEventCreate(&t.ev[i]));
     if (!t.zmap_valid) TCK(tc2_zmap(t, s, m, grid_cap, st));
     const long long sub = t.sub_batch > 0 ? t.sub_batch : 524288;
-    const size_t need = (size_t)(((sub + ROWS - 1) / ROWS) * ROWS) * HID * sizeof(float);
+    const size_t need = t.fused ? 0 : (size_t)(((sub + ROWS - 1) / ROWS) * ROWS) * HID * sizeof(float);
     if (need > t.scratch_bytes) {
         if (t.scratch) cudaFree(t.scratch);
         t.scratch = nullptr; t.scratch_bytes = 0;
@@ -1040,7 +1086,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.steps[n++] = GemmStep{1, 2, 256, COL_X, 0, 2, tl};                            // lin_in; followed by the gather of Y_0 (K block 0)
     for (int b = 0; b < t.n_pre; ++b) {
         pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0, tl};             // fc_0[b]
-        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 1, tl};               // fc_1[b]; overlapped by the gather of Y_{b+1} / the next tile's Y_0
+        pre.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, (short)(b + 1 < t.n_pre ? 1 : 3), tl};   // fc_1[b]; overlapped by the gather of Y_{b+1} / the next tile's Y_0
     }
     pre.n_steps = n;
     n = 0;
@@ -1066,6 +1112,35 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     if (t.dbg_skip & 512) TCK(cudaMemsetAsync(dbg_ts, 0, 8 * 64 * sizeof(long long), st));
     pre.dbg_ts = (t.dbg_skip & 512) ? dbg_ts : nullptr; post.dbg_ts = nullptr;
     t.ms_pre = t.ms_post = 0.f;
+    if (t.fused) {
+        // ONE launch for the whole call: per 64 samples, NV PRE tiles then the POST tile; x_c goes through a 128 KiB slab per CTA
+        // (L2 resident) instead of the sub-batch sized scratch, and the per-sample (rgb, sigma) rows are the only output
+        Args f = pre;
+        for (int i = 0; i < post.n_steps; ++i) f.steps_post[i] = post.steps[i];
+        f.n_steps_post = post.n_steps; f.n_blocks_post = post.n_blocks; f.uses_post = post.uses_per_tile;
+        f.tile_table_post = post.tile_table; f.bias_post = post.bias;
+        f.ppr = NV;
+        f.s_begin = 0; f.n_samples = total;
+        f.n_tiles = (total + ROWS - 1) / ROWS;
+        const long long g = ((f.n_tiles + 1) / 2) * 2;
+        const int grid = (int)(g < grid_cap ? g : grid_cap);
+        const size_t slab = (size_t)grid * ROWS * HID * sizeof(float);
+        if (slab > t.scratch_bytes) {
+            if (t.scratch) cudaFree(t.scratch);
+            t.scratch = nullptr; t.scratch_bytes = 0;
+            TCK(cudaMalloc(&t.scratch, slab));
+            t.scratch_bytes = slab;
+        }
+        f.xc = (float*)t.scratch;
+        if (t.timing) TCK(cudaEventRecord(t.ev[0], st));
+        if (parity) TCK((launch<true, KIND_FUSED>(f, grid, st))); else TCK((launch<false, KIND_FUSED>(f, grid, st)));
+        if (t.timing) {
+            TCK(cudaEventRecord(t.ev[1], st));
+            TCK(cudaEventSynchronize(t.ev[1]));
+            TCK(cudaEventElapsedTime(&t.ms_pre, t.ev[0], t.ev[1]));
+        }
+        return cudaSuccess;
+    }
     for (long long s0 = 0; s0 < total; s0 += sub) {
         const long long ns = total - s0 < sub ? total - s0 : sub;
         pre.s_begin = post.s_begin = s0;

@@ -398,6 +398,10 @@ def test_pair_kernel_pipeline_shape_sweep(NV, SB, K, nr):
     assert e_rgb <= PAR_TOL and e_d <= PAR_TOL
     _, rgb_s, _ = ctx.composite(rays, z, True, 2, want_weights=False)       # fast mode runs the same protocol with other timings
     assert bool(torch.isfinite(rgb_s).all()) and float((rgb_s - rgb_f).abs().max()) < 1e-2
+    ctx.set_option("fused", 0)                                              # PRE / POST launches with the HBM scratch: same arithmetic
+    _, rgb_u, d_u = ctx.composite(rays, z, True, 1, want_weights=False)
+    assert torch.equal(rgb_u, rgb_p) and torch.equal(d_u, d_p), "fused and two-kernel paths differ"
+    ctx.set_option("fused", 1)
     for tail in (0, 4):                                                     # the other MMA issue orders must give the same bits
         ctx.set_option("tail_kb", tail)
         _, rgb_t, d_t = ctx.composite(rays, z, True, 1, want_weights=False)
