@@ -503,6 +503,9 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     if (!strcmp(key, "fused")) {
         if (value != 0 && value != 1) return fail(DINER_E_INVALID, "fused must be 0 or 1");
         c->tc.fused = (int)value;
+    } else if (!strcmp(key, "post_tiles")) {
+        if (value < 1 || value > 8) return fail(DINER_E_INVALID, "post_tiles must be in [1,8]");
+        c->tc.post_tiles = (int)value;
     } else if (!strcmp(key, "tail_kb")) {
         if (value < 0 || value > 4) return fail(DINER_E_INVALID, "tail_kb must be in [0,4]");
         c->tc.tail_kb = (int)value;

@@ -40,6 +40,8 @@
 // Reference semantics: src/models/resnetfc.py:61-69,129-159; src/models/pixelnerf.py:91-143; src/models/image_encoder.py:97-146.
 #include "mlp_tc.h"
 
+#include <algorithm>
+
 namespace tc2 {
 
 using tc::smem_u32;
@@ -116,10 +118,11 @@ struct Args {
     const float* bias2;         // pair-kernel PRE rows: [0,n_pre) bias folded into Y_b, row n_pre = b_fc1[n_pre-1] (added at the combine)
     GemmStep steps[MAX_STEPS];
     int n_steps, n_blocks, uses_per_tile;
-    // FUSED launch: a round = ppr PRE tiles (ppr * spv = 64 samples) followed by ONE POST tile over the same 64 samples; the view-combined
-    // activations x_c go through a per-CTA slab of `xc` (64 x 512 fp32 = 128 KiB, L2 resident) instead of a sub-batch sized HBM scratch
+    // FUSED launch: a round = ppr PRE tiles (ppr * spv = 64 * pts samples) followed by pts POST tiles over the same samples; the view-combined
+    // activations x_c go through a per-CTA slab of `xc` (64 * pts rows x 512 fp32, L2 resident) instead of a sub-batch sized HBM scratch.
+    // Only the first PRE tile of a round starts cold (the POST tiles own the operand buffers), so pts > 1 amortises that start.
     GemmStep steps_post[2 * DINER_MAX_BLOCKS + 1];
-    int n_steps_post, n_blocks_post, uses_post, ppr;
+    int n_steps_post, n_blocks_post, uses_post, ppr, pts;
     const int* tile_table_post;
     const float* bias_post;
     long long s_begin, n_samples, n_total, n_tiles;   // n_tiles counts 64-row CTA tiles
@@ -523,6 +526,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + C::OFF_BARS + 8 * (2 * C::NST + 4 + HID / KBLK));
 
     if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 90); __trap(); }
+    const long long clk_start = a.dbg_ts ? clock64() : 0;
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_opnd, NUM_WORKER_WARPS + 1);
@@ -546,7 +550,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     // both CTAs of a pair run the same number of rounds; CTA tile = 2 * pair_tile + rank
     const long long first = (long long)blockIdx.x, stride = (long long)gridDim.x;
     const long long n_rounds = (a.n_tiles + stride - 1) / stride;
-    const int uses_per_round = FUSED ? a.ppr * a.uses_per_tile + a.uses_post : a.uses_per_tile;
+    const int uses_per_round = FUSED ? a.ppr * a.uses_per_tile + a.pts * a.uses_post : a.uses_per_tile;
     const long long total_uses = n_rounds * uses_per_round;
 
     const int prod_idx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
@@ -566,7 +570,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 mbar_wait(bar_empty + 8 * st, ph ^ 1, a.err, 10);
                 if (leader) {
                     const int tix = (!FUSED || t < a.ppr * a.uses_per_tile) ? __ldg(table + t % a.uses_per_tile)
-                                                                            : __ldg(table_post + (t - a.ppr * a.uses_per_tile));
+                                                                            : __ldg(table_post + (t - a.ppr * a.uses_per_tile) % a.uses_post);
                     const bool small = (tix & TILE_SMALL) != 0;          // lin_out: only the first 16 rows of the tile are read
                     const int row = (tix & (TILE_SMALL - 1)) * 128;
                     if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, small ? 2 * SMALL_TILE_BYTES : 2 * WTILE_BYTES);
@@ -665,7 +669,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         for (long long rd = 0; rd < n_rounds; ++rd) {
             if constexpr (FUSED) {
                 for (int j = 0; j < a.ppr; ++j) run_steps(a.steps, a.n_steps, j == 0, j + 1 < a.ppr, rd * a.ppr + j);
-                run_steps(a.steps_post, a.n_steps_post, false, false, -1);
+                for (int k = 0; k < a.pts; ++k) run_steps(a.steps_post, a.n_steps_post, false, false, -1);
             } else {
                 run_steps(a.steps, a.n_steps, rd == 0, rd + 1 < n_rounds, rd);
             }
@@ -687,6 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             // K blocks 1..7, were produced during the previous tile's last block; its lin_in was handed off after that tile's combine.
             int tsn = 0; (void)tsn;
             const long long rd = pt; (void)rd;
+            if (a.dbg_ts && blockIdx.x < 4 && wwarp == 0 && lane == 0) a.dbg_ts[512 + blockIdx.x * 512 + (pt < 511 ? pt : 511)] = clock64();
             const Tap* tp = taps + (pt & 1) * ROWS;
             Tap* tn = taps + ((pt + 1) & 1) * ROWS;
             if (cold) {
@@ -911,14 +916,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             } else if constexpr (KIND == KIND_POST) {
                 post_tile(tile, live, a.bias, a.n_blocks, 0);
             } else {
-                // FUSED: a.n_tiles counts 64-sample rounds; PRE tile j covers samples [64 * tile + j * spv, + spv)
-                const long long slab = (long long)blockIdx.x * ROWS;
+                // FUSED: a.n_tiles counts rounds of 64 * pts samples; PRE tile j covers samples [64 * pts * tile + j * spv, + spv)
+                const long long slab = (long long)blockIdx.x * ROWS * a.pts;
                 for (int j = 0; j < a.ppr; ++j)
                     pre_tile(tile * a.ppr + j, live, j == 0, j + 1 < a.ppr, tile * a.ppr + j + 1, rd * a.ppr + j, slab + (long long)j * a.spv);
-                post_tile(tile, live, a.bias_post, a.n_blocks_post, slab);
+                for (int k = 0; k < a.pts; ++k) post_tile(tile * a.pts + k, live, a.bias_post, a.n_blocks_post, slab + (long long)k * ROWS);
             }
         }
     }
+    if (a.dbg_ts && threadIdx.x == 0 && blockIdx.x < 256) a.dbg_ts[2560 + blockIdx.x] = clock64() - clk_start;
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -1041,6 +1047,8 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
     return cudaSuccess;
 }
 
+static cudaError_t tc2_dump_stamps(const long long* dev, cudaStream_t st);
+
 cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const QueryArgs& q, bool parity, int num_sms,
                       cudaStream_t st) {
     using namespace tc2;
@@ -1108,8 +1116,8 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     pre.worker_kb_hi = t.tail_kb > 0 ? HID / KBLK - 1 - t.tail_kb : 4;
     pre.early_worker_kb_hi = t.early_split > 0 ? t.early_split : pre.worker_kb_hi;
     static long long* dbg_ts = nullptr;      // device memory (managed memory would page-fault inside the kernel and distort the timeline)
-    if ((t.dbg_skip & 512) && !dbg_ts) TCK(cudaMalloc((void**)&dbg_ts, 8 * 64 * sizeof(long long)));
-    if (t.dbg_skip & 512) TCK(cudaMemsetAsync(dbg_ts, 0, 8 * 64 * sizeof(long long), st));
+    if ((t.dbg_skip & 512) && !dbg_ts) TCK(cudaMalloc((void**)&dbg_ts, 4096 * sizeof(long long)));
+    if (t.dbg_skip & 512) TCK(cudaMemsetAsync(dbg_ts, 0, 4096 * sizeof(long long), st));
     pre.dbg_ts = (t.dbg_skip & 512) ? dbg_ts : nullptr; post.dbg_ts = nullptr;
     t.ms_pre = t.ms_post = 0.f;
     if (t.fused) {
@@ -1119,12 +1127,13 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         for (int i = 0; i < post.n_steps; ++i) f.steps_post[i] = post.steps[i];
         f.n_steps_post = post.n_steps; f.n_blocks_post = post.n_blocks; f.uses_post = post.uses_per_tile;
         f.tile_table_post = post.tile_table; f.bias_post = post.bias;
-        f.ppr = NV;
+        f.pts = t.post_tiles > 0 ? t.post_tiles : 1;
+        f.ppr = NV * f.pts;
         f.s_begin = 0; f.n_samples = total;
-        f.n_tiles = (total + ROWS - 1) / ROWS;
+        f.n_tiles = (total + (long long)ROWS * f.pts - 1) / ((long long)ROWS * f.pts);
         const long long g = ((f.n_tiles + 1) / 2) * 2;
         const int grid = (int)(g < grid_cap ? g : grid_cap);
-        const size_t slab = (size_t)grid * ROWS * HID * sizeof(float);
+        const size_t slab = (size_t)grid * ROWS * f.pts * HID * sizeof(float);
         if (slab > t.scratch_bytes) {
             if (t.scratch) cudaFree(t.scratch);
             t.scratch = nullptr; t.scratch_bytes = 0;
@@ -1139,6 +1148,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
             TCK(cudaEventSynchronize(t.ev[1]));
             TCK(cudaEventElapsedTime(&t.ms_pre, t.ev[0], t.ev[1]));
         }
+        if (f.dbg_ts) TCK(tc2_dump_stamps(f.dbg_ts, st));
         return cudaSuccess;
     }
     for (long long s0 = 0; s0 < total; s0 += sub) {
@@ -1162,10 +1172,36 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
             t.ms_pre += x; t.ms_post += y;
         }
     }
-    if (pre.dbg_ts) {
-        static long long h[8 * 64];
+    if (pre.dbg_ts) TCK(tc2_dump_stamps(pre.dbg_ts, st));
+    return cudaSuccess;
+}
+
+// profiling (DINER_TC_DBG_SKIP=512): timeline of CTA pair 0 in round TS_ROUND, PRE-tile periods of CTAs 0..3, per-CTA kernel cycles
+static cudaError_t tc2_dump_stamps(const long long* dev, cudaStream_t st) {
+    {
+        static long long h[4096];
         TCK(cudaStreamSynchronize(st));
-        TCK(cudaMemcpy(h, pre.dbg_ts, sizeof(h), cudaMemcpyDeviceToHost));
+        TCK(cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int cta = 0; cta < 4; ++cta) {
+            std::vector<long long> d;
+            for (int i = 1; i < 511 && h[512 + cta * 512 + i]; ++i) d.push_back(h[512 + cta * 512 + i] - h[512 + cta * 512 + i - 1]);
+            if (d.empty()) continue;
+            std::vector<long long> s = d;
+            std::sort(s.begin(), s.end());
+            double mean = 0;
+            for (long long v : d) mean += (double)v;
+            fprintf(stderr, "[ts] cta %d PRE-tile periods (cycles, %d tiles): min %lld  p10 %lld  median %lld  mean %.0f  p90 %lld  max %lld | first 6:", cta,
+                    (int)d.size(), s.front(), s[s.size() / 10], s[s.size() / 2], mean / d.size(), s[s.size() * 9 / 10], s.back());
+            for (size_t i = 0; i < 6 && i < d.size(); ++i) fprintf(stderr, " %lld", d[i]);
+            fprintf(stderr, "\n");
+        }
+        std::vector<long long> tot;
+        for (int i = 0; i < 256; ++i) if (h[2560 + i]) tot.push_back(h[2560 + i]);
+        if (!tot.empty()) {
+            std::sort(tot.begin(), tot.end());
+            fprintf(stderr, "[ts] kernel cycles per CTA (%d CTAs): min %lld  median %lld  max %lld  (max/min %.3f)\n", (int)tot.size(), tot.front(),
+                    tot[tot.size() / 2], tot.back(), (double)tot.back() / (double)tot.front());
+        }
         for (int cta = 0; cta < 2; ++cta) {
             const long long t0 = h[(cta * 4 + 1) * 64];
             fprintf(stderr, "[ts] cta %d worker-warp-0 stamps of round %d, cycles since the first:", cta, TS_ROUND);
