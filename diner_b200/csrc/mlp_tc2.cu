@@ -263,17 +263,34 @@ __device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, ui
         taps[r] = rt;
     }
     if (FEAT) {
-        rotate_to_cam(p, dx, dy, dz, dxc, dyc, dzc);
-        const float dd = __fsub_rn(lookup_depth(s, sv, u, w), zc);
-        const int d_in = 3 + 6 * s.num_freqs + 3 + 1 + 2 * s.num_freqs;
-#pragma unroll 1
-        for (int e = part; e < KBLK; e += PARTS) {
-            const float val = e < d_in ? feature_elem(e, s.num_freqs, s.freqs, xc, yc, zc, dxc, dyc, dzc, dd) : 0.0f;
+        // lin_in input columns of this row (same values and order as feature_elem, mlp_simt.cu):
+        //   [x_c y_c z_c | per frequency k: sin(f_k xyz) cos(f_k xyz) | dir_c xyz | dd | per frequency k: sin(f_k dd) cos(f_k dd) | 0 ...]
+        // The PARTS threads of a row split the FREQUENCIES: the 8 sin evaluations of one frequency are independent, so they pipeline
+        // (one element at a time through a branchy selector cost ~20 k cycles per tile on the four helper warps).
+        const int F = s.num_freqs, npe = 6 * F, d_in = 3 + npe + 3 + 1 + 2 * F;
+        auto put = [&](int e, float val) {
             __half hi, lo;
             split1(val, hi, lo);
             const uint32_t off = act_off(r, e >> 3) + (uint32_t)(e & 7) * 2u;
             *(__half*)(Ahi + off) = hi;
             if (PARITY) *(__half*)(Alo + off) = lo;
+        };
+        const float dd = __fsub_rn(lookup_depth(s, sv, u, w), zc);
+#pragma unroll 1
+        for (int k = part; k < F; k += PARTS) {
+            const float f = s.freqs[k];
+            const float v0 = pe_sin(xc, f), v1 = pe_sin(yc, f), v2 = pe_sin(zc, f), v3 = pe_cos(xc, f), v4 = pe_cos(yc, f), v5 = pe_cos(zc, f);
+            const float v6 = pe_sin(dd, f), v7 = pe_cos(dd, f);
+            const int e0 = 3 + 6 * k, e1 = 7 + npe + 2 * k;
+            put(e0, v0); put(e0 + 1, v1); put(e0 + 2, v2); put(e0 + 3, v3); put(e0 + 4, v4); put(e0 + 5, v5);
+            put(e1, v6); put(e1 + 1, v7);
+        }
+        if (part == PARTS - 1) {
+            rotate_to_cam(p, dx, dy, dz, dxc, dyc, dzc);
+            put(0, xc); put(1, yc); put(2, zc);
+            put(3 + npe, dxc); put(4 + npe, dyc); put(5 + npe, dzc);
+            put(6 + npe, dd);
+            for (int e = d_in; e < KBLK; ++e) put(e, 0.0f);
         }
     }
 }
@@ -430,6 +447,23 @@ __device__ __forceinline__ void store_y_rows(uint32_t tmem, float* __restrict__ 
     }
 }
 
+// L2 residency of the FUSED launch's x_c slab (148 x 128 KiB): the Y-map gather streams gigabytes through the L2 and would evict the
+// slab's dirty lines to HBM (ncu: 0.47 GB of write-backs per 524 288 samples without the hint); evict_last keeps them.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v, uint64_t pol) {
+    if (pol) asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+    else *(float4*)p = v;
+}
+__device__ __forceinline__ float4 ld_f4_l2(const float4* p, uint64_t pol) {     // data written by this kernel: L2 only, never the read-only path
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+
 // View-combine of 32 accumulator columns: reduce-scatter over the NV adjacent lanes (rows) of a sample.  After it, lane j of the
 // group holds 32/NV consecutive columns starting at the returned offset (summed over the NV views, pairwise order).
 template <int NV>
@@ -453,7 +487,7 @@ __device__ __forceinline__ int combine_lanes(float (&v)[32], int lane) {
 }
 template <int NV>
 __device__ __forceinline__ void combine_store(uint32_t* raw, const float* __restrict__ cb, int h0, int lane, float* dst_sample, bool write,
-                                              int nv_real) {
+                                              int nv_real, uint64_t pol) {
     float v[32];
     const bool pad_row = (lane & (NV - 1)) >= nv_real;          // row of a padding view: contributes nothing to the mean
 #pragma unroll
@@ -467,7 +501,7 @@ __device__ __forceinline__ void combine_store(uint32_t* raw, const float* __rest
         float* dst = dst_sample + h0 + off;
         if constexpr (CNT >= 4) {
 #pragma unroll
-            for (int i = 0; i < CNT; i += 4) *(float4*)(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < CNT; i += 4) st_f4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]), pol);
         } else {
 #pragma unroll
             for (int i = 0; i < CNT; ++i) dst[i] = v[i];
@@ -502,6 +536,7 @@ __device__ __forceinline__ void opnd_warps_join() {
 
 #define TS_ROUND 20     // a steady-state round (the first rounds of a launch gather cold Y-map lines from HBM)
 #define TS(role, slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && lane == 0) a.dbg_ts[(blockIdx.x * 4 + (role)) * 64 + (slot)] = clock64(); } while (0)
+#define TSH(slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && wwarp == NUM_WORKER_WARPS && lane == 0) a.dbg_ts[(blockIdx.x * 4 + 2) * 64 + (slot)] = clock64(); } while (0)
 #define TSW() do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && wwarp == 0 && lane == 0 && tsn < 64) a.dbg_ts[(blockIdx.x * 4 + 1) * 64 + tsn++] = clock64(); } while (0)
 // ---- the kernel ----------------------------------------------------------------------------------
 constexpr int KIND_PRE = 0, KIND_POST = 1, KIND_ZMAP = 2, KIND_FUSED = 3;
@@ -682,6 +717,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const int q = warp & 3, n2 = (wwarp >> 2) & 1;
         const int r = 32 * (q & 1) + lane;
         uint32_t it = 0, ph0 = 0, ph1 = 0;   // phase counters: bar_acc, bar_afree[0], bar_afree[1..7]
+        const uint64_t slab_pol = FUSED ? l2_evict_last_policy() : 0;
         (void)ph0; (void)ph1;
         // One PRE tile (64 sample-view rows).  cold: nothing was prepared by a previous tile; has_next: tile_next follows in the
         // pipeline (its taps / features / Y_0 are produced under this tile's last block); pt: running PRE tile count (tap buffer
@@ -749,14 +785,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     // next tile, under the last fc_1: lin_in features into K block 0 as soon as fc_1 has consumed it (helpers),
                     // Y_0 staging of K blocks 1..7 as they are released (everyone)
                     if (helper) {
+                        TSH(0);
                         mbar_wait(bar_afree, ph0 & 1, a.err, 47);
+                        TSH(1);
                         prep_rows<PARITY, NUM_HELPER_WARPS * 32 / 64, false, true>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                        TSH(2);
                         fence_proxy_async();
                         asm volatile("bar.arrive 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                    // features in place
                     } else {
                         asm volatile("bar.sync 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                      // next taps in place
                     }
                     gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.early_worker_kb_hi);
+                    if (helper) TSH(3); else TSW();
                     // workers consume K block 0's phase too (the helpers did above -- and must NOT wait on it again here: by the time
                     // they finish their late K blocks, lin_in of the next tile may already have completed the barrier's next phase)
                     if (!helper) mbar_wait(bar_afree, ph0 & 1, a.err, 48);
@@ -786,18 +826,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
                 const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
                 switch (a.NV) {
-                    case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                    case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                    case 4: combine_store<4>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                    case 8: combine_store<8>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                    case 16: combine_store<16>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
-                    default: combine_store<32>(v, cb, h0, lane, dst_sample, wr, a.NV_real); break;
+                    case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
+                    case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
+                    case 4: combine_store<4>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
+                    case 8: combine_store<8>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
+                    case 16: combine_store<16>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
+                    default: combine_store<32>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
                 }
             }
             tc_fence_before();
+            TSW();
             if (has_next && !helper) {
                 asm volatile("bar.sync 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // next tile's features in place
+                TSW();
                 worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // X read out -> lin_in of the next tile
+                TSW();
             }
             if (FUSED && !has_next && !helper) {
                 // the POST tile overwrites TMEM X and the whole A operand: the last fc_1 must be complete (the n2 == 0 warps only
@@ -819,7 +862,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 uint32_t v[32];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 f = FUSED ? __ldcg(src + i) : __ldg(src + i);     // FUSED: written by this kernel -> no read-only path
+                    const float4 f = FUSED ? ld_f4_l2(src + i, slab_pol) : __ldg(src + i);     // FUSED: written by this kernel -> no read-only path
                     v[4 * i] = __float_as_uint(f.x * W_SCALE); v[4 * i + 1] = __float_as_uint(f.y * W_SCALE);
                     v[4 * i + 2] = __float_as_uint(f.z * W_SCALE); v[4 * i + 3] = __float_as_uint(f.w * W_SCALE);
                 }
@@ -1206,6 +1249,9 @@ static cudaError_t tc2_dump_stamps(const long long* dev, cudaStream_t st) {
             const long long t0 = h[(cta * 4 + 1) * 64];
             fprintf(stderr, "[ts] cta %d worker-warp-0 stamps of round %d, cycles since the first:", cta, TS_ROUND);
             for (int i = 0; i < 40 && h[(cta * 4 + 1) * 64 + i]; ++i) fprintf(stderr, " %lld", h[(cta * 4 + 1) * 64 + i] - t0);
+            fprintf(stderr, "\n");
+            fprintf(stderr, "[ts] cta %d helper-warp-0 stamps of the last block (at the kb-0 wait, past it, features done, early gather done):", cta);
+            for (int i = 0; i < 4; ++i) fprintf(stderr, " %lld", h[(cta * 4 + 2) * 64 + i] ? h[(cta * 4 + 2) * 64 + i] - t0 : 0);
             fprintf(stderr, "\n");
             if (cta == 0) {
                 fprintf(stderr, "[ts] cta 0 mma stamps per step (half 0 ready, half 1 ready, committed, -), same origin:");

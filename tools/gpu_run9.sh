@@ -1,0 +1,10 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 --tb=short -k "sweep or query_stagewise or properties_and_edges" 2>&1 | tail -4
+for F in 0 1; do
+DINER_TC_FUSED=$F DINER_TC_DBG_SKIP=512 timeout 300 python tools/profile_run.py parity 8192 1 2>&1 | grep -E "ts\]|rep" | cut -c1-420 | tee gpurun_out/r2i_ts_fused$F.log
+done
+for F in 1 0; do
+  DINER_TC_FUSED=$F timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2i_bench_fused$F.json 2> gpurun_out/r2i_bench_fused$F.err
+  python -c "
+import json;d=json.load(open('gpurun_out/r2i_bench_fused$F.json'));print('fused',$F,d['value'],d['e2e']['value'],d['roofline']['frac'],d['roofline']['stage_ms_per_step'],d['clocks'],d['gpu_launches'])"
+done
