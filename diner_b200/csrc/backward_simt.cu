@@ -9,8 +9,15 @@
 // network output; (2) per chunk of samples the fp32 forward is recomputed with every block input kept, then the chain is
 // walked backwards with the same 64x64-tile GEMM kernel (data gradients use transposed weight copies) and a split-K
 // weight-gradient kernel that accumulates with atomics; (3) the gradient of the gathered latent rows is scattered back
-// through the bilinear taps.  A tcgen05 version reuses this as its parity anchor, like the forward modes do.
+// through the bilinear taps.
+//
+// Two arithmetic paths share this chain: fp32 CUDA cores (the 64x64-tile kernels below; parity anchor, any MLP shape), and --
+// for the shipped 512-wide network -- the tcgen05 GEMM of gemm_tc3.cu (fp16 hi/lo split operands, fp32 accumulation: the same
+// arithmetic as the forward parity mode) for every 512x512 GEMM: forward recompute, data gradients (packed transposed weights)
+// and weight gradients (G^T against packed activations, split over the rows, atomics).  The few narrow GEMMs (lin_in: 55
+// inputs, lin_out: 4 outputs) stay on the CUDA cores.
 #include "diner_internal.h"
+#include "mlp_tc.h"
 
 namespace {
 
@@ -230,14 +237,25 @@ size_t backward_workspace_bytes(const MlpDev& m, const SceneDev& s, long long ch
     return f * sizeof(float);
 }
 
+// workspace of the tcgen05 path: packed transposed weights, G^T (512 x R fp32) and two packed activation buffers (R x 2 KiB each)
+size_t backward_tc_workspace_bytes(const MlpDev& m, const SceneDev& s, long long chunk_samples) {
+    const long long R = chunk_samples * s.NV;
+    const long long nkb = (R + 63) / 64;
+    const int n_pre = m.combine_layer < m.n_blocks ? m.combine_layer : m.n_blocks;
+    const size_t wt = (size_t)(2 * m.n_blocks + n_pre) * 4 * 8 * 2 * tc::WTILE_BYTES;
+    return wt + (size_t)512 * (size_t)(nkb * 64) * sizeof(float) + 2 * (size_t)(4 * nkb) * 2 * tc::WTILE_BYTES + 4096;
+}
+
 // d_pre (n,4): pre-activation gradients of the per-sample outputs (composite_backward_kernel).  grad_params / d_latent are
-// ACCUMULATED into (the caller zeroes them).  ws = workspace of backward_workspace_bytes(chunk).
+// ACCUMULATED into (the caller zeroes them).  ws = workspace of backward_workspace_bytes(chunk); tcs / tcws != nullptr selects
+// the tcgen05 GEMMs (tcws = workspace of backward_tc_workspace_bytes(chunk), needs the 512-wide network packed in tcs).
 cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q, const float* d_pre, float* grad_params,
-                          float* d_latent, float* ws, long long chunk, cudaStream_t st) {
+                          float* d_latent, float* ws, long long chunk, cudaStream_t st, TcState* tcs, uint8_t* tcws, int num_sms) {
     const long long total = (long long)q.SB * q.n_per_sb;
     const int Hd = m.d_hidden, L = m.d_latent, ld_in = (m.d_in + 7) & ~7;
     const int n_pre = m.combine_layer < m.n_blocks ? m.combine_layer : m.n_blocks, n_post = m.n_blocks - n_pre;
     if (n_post < 1 || n_pre < 1) return cudaErrorNotSupported;
+    const bool use_tc = tcs && tcws && tcs->ready && tcs->wmap_ok && Hd == 512 && L == 512;
     // ---- gradient buffer slices (same order as the parameter store)
     float* gp = grad_params;
     auto take = [&](size_t n) { float* p = gp; gp += n; return p; };
@@ -282,6 +300,89 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
     for (int b = 0; b < m.n_blocks; ++b) { BK(transpose(m.w_fc0[b], wT0[b], Hd, Hd)); BK(transpose(m.w_fc1[b], wT1[b], Hd, Hd)); }
     for (int b = 0; b < n_pre; ++b) BK(transpose(m.w_z[b], wTz[b], Hd, L));
 
+    // ---- tcgen05 path: packed transposed weights, tile-pair offsets of the forward weights in tcs->wpack, GEMM wrappers
+    const long long Rmax = chunk * s.NV, nkb_max = (Rmax + 63) / 64;
+    const int grid_pairs = num_sms / 2;
+    uint8_t* wt_pack = tcws;                                                       // [2 n_blocks + n_pre][4 x 8 tile pairs]
+    const size_t layer_bytes = (size_t)4 * 8 * 2 * tc::WTILE_BYTES;
+    float* GT = use_tc ? (float*)(tcws + (size_t)(2 * m.n_blocks + n_pre) * layer_bytes) : nullptr;      // (512, nkb_max * 64)
+    uint8_t* AP = use_tc ? (uint8_t*)(GT + (size_t)512 * nkb_max * 64) : nullptr;                         // packed activations
+    uint8_t* ZP = use_tc ? AP + (size_t)(4 * nkb_max) * 2 * tc::WTILE_BYTES : nullptr;                   // packed zlat (shared by the lin_z blocks)
+    float* gscale = use_tc ? (float*)(ZP + (size_t)(4 * nkb_max) * 2 * tc::WTILE_BYTES) : nullptr;        // {s, 1/s, amax bits}: loss scaling of the gradient operands
+    if (use_tc) {
+        BK(cudaMemsetAsync(gscale, 0, 16, st));
+        tc3::absmax_kernel<<<296, 256, 0, st>>>(d_pre, total * 4, (unsigned int*)(gscale + 2));
+        tc3::make_scale_kernel<<<1, 1, 0, st>>>((const unsigned int*)(gscale + 2), gscale);
+        g_launches += 2;
+        BK(cudaGetLastError());
+    }
+    static Tc3Map map_wt, map_ap, map_zp;
+    long long pair_in = 0, pair_z[DINER_MAX_BLOCKS], pair_0[DINER_MAX_BLOCKS], pair_1[DINER_MAX_BLOCKS];   // offsets in tcs->wpack (tc_pack_weights order)
+    {
+        long long p = tc::MT * 1;                                                  // lin_in
+        (void)pair_in;
+        for (int b = 0; b < n_pre; ++b) { pair_z[b] = p; p += tc::MT * (L / 64); pair_0[b] = p; p += tc::MT * 8; pair_1[b] = p; p += tc::MT * 8; }
+        for (int b = n_pre; b < m.n_blocks; ++b) { pair_0[b] = p; p += tc::MT * 8; pair_1[b] = p; p += tc::MT * 8; }
+    }
+    auto wt_pair = [&](int idx) { return (long long)idx * 4 * 8; };                // idx: 2b = W0^T of block b, 2b+1 = W1^T, 2 n_blocks + b = Wz^T
+    if (use_tc) {
+        auto packT = [&](const float* wT, int idx) -> cudaError_t {              // wT is (in, out) row-major = the "weight" of the data-gradient GEMM
+            tc::pack_weight_kernel<<<4 * 8, 256, 0, st>>>(wT, 512, 512, 8, wt_pack + (size_t)idx * layer_bytes);
+            g_launches++;
+            return cudaGetLastError();
+        };
+        for (int b = 0; b < m.n_blocks; ++b) { BK(packT(wT0[b], 2 * b)); BK(packT(wT1[b], 2 * b + 1)); }
+        for (int b = 0; b < n_pre; ++b) BK(packT(wTz[b], 2 * m.n_blocks + b));
+        BK(tc3_make_map(map_wt, wt_pack, (size_t)(2 * m.n_blocks + n_pre) * layer_bytes));
+        BK(tc3_make_map(map_ap, AP, (size_t)(4 * nkb_max) * 2 * tc::WTILE_BYTES));
+        BK(tc3_make_map(map_zp, ZP, (size_t)(4 * nkb_max) * 2 * tc::WTILE_BYTES));
+    }
+    // Y (rows x 512) (+)= act(X (rows x 512)) . W^T + bias   [forward weights packed in tcs->wpack]
+    auto tc_fwd = [&](const float* X, bool relu_in, long long pair0, const float* bias, float* Y, bool accum, long long rows) -> cudaError_t {
+        tc3::Args a{};
+        a.bmap = tcs->wmap; a.A = X; a.lda = 512; a.rows = rows; a.K = 512; a.nkb_total = 8; a.relu_a = relu_in; a.b_pair0 = pair0;
+        a.n_slices = 1; a.kb_per_slice = 8; a.C = Y; a.ldc = 512; a.mode = accum ? 1 : 0; a.scale = tc::W_INV; a.bias = bias;
+        return tc3_gemm(a, grid_pairs, tcs->err_flag, st);
+    };
+    // GX (rows x 512) (+)= (G (rows x 512) . W) * (mask > 0)   [W^T packed in wt_pack]
+    auto tc_dgrad = [&](const float* G, int idx, const float* mask, float* GX, bool accum, long long rows) -> cudaError_t {
+        tc3::Args a{};
+        a.bmap = map_wt.map; a.A = G; a.lda = 512; a.rows = rows; a.K = 512; a.nkb_total = 8; a.relu_a = 0; a.b_pair0 = wt_pair(idx);
+        a.n_slices = 1; a.kb_per_slice = 8; a.C = GX; a.ldc = 512; a.mode = accum ? 1 : 0; a.scale = tc::W_INV; a.mask = mask; a.ldm = 512;
+        a.a_scale = gscale;
+        return tc3_gemm(a, grid_pairs, tcs->err_flag, st);
+    };
+    // packs act(X)^T (rows x 512) into `dst` as the B operand of a weight-gradient GEMM
+    auto tc_pack_act = [&](const float* X, bool relu, long long rows, uint8_t* dst) -> cudaError_t {
+        const long long nkb = (rows + 63) / 64;
+        tc3::pack_rows_kernel<<<(unsigned)(4 * nkb), 256, 0, st>>>(X, 512, rows, (int)nkb, relu ? 1 : 0, dst);
+        g_launches++;
+        return cudaGetLastError();
+    };
+    // dW (512 x 512) += G^T . act(X);  db += column sums of G.  `packed` = tc_pack_act(X) (AP or ZP)
+    auto tc_wgrad = [&](const float* G, const Tc3Map& pmap, long long rows, float* dW, float* db) -> cudaError_t {
+        const long long nkb = (rows + 63) / 64;
+        dim3 tg(512 / 32, (unsigned)(nkb * 2)), tb(32, 8);
+        tc3::transpose_pad_kernel<<<tg, tb, 0, st>>>(G, GT, rows, 512, nkb * 64);   // (rows, 512) -> (512, nkb * 64), zero padded
+        g_launches++;
+        tc3::Args a{};
+        a.bmap = pmap.map; a.A = GT; a.lda = nkb * 64; a.rows = 512; a.K = rows; a.nkb_total = (int)nkb; a.relu_a = 0; a.b_pair0 = 0;
+        a.a_scale = gscale;
+        int slices = grid_pairs / 4 > 0 ? grid_pairs / 4 : 1;                      // 4 row tiles of 128 outputs x K slices ~ one item per CTA pair
+        if (slices > nkb) slices = (int)nkb;
+        a.kb_per_slice = (int)((nkb + slices - 1) / slices);
+        a.n_slices = (int)((nkb + a.kb_per_slice - 1) / a.kb_per_slice);
+        a.C = dW; a.ldc = 512; a.mode = 2; a.scale = 1.0f;
+        BK(tc3_gemm(a, grid_pairs, tcs->err_flag, st));
+        if (db) {
+            const long long per = 256;                                                  // 2 x rows/256 CTAs: enough loads in flight for HBM
+            dim3 cg(2, (unsigned)((rows + per - 1) / per));
+            tc3::colsum_kernel<<<cg, 256, 0, st>>>(G, 512, rows, 512, per, db);
+            g_launches++;
+        }
+        return cudaGetLastError();
+    };
+
     for (long long s0 = 0; s0 < total; s0 += chunk) {
         const long long ns = total - s0 < chunk ? total - s0 : chunk;
         const long long R = ns * s.NV;
@@ -292,6 +393,13 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         BK(cudaGetLastError());
         BK((linear<false, false>(xin, ld_in, m.w_in, m.d_in, m.b_in, x, Hd, R, m.d_in, Hd, st)));
         for (int b = 0; b < n_pre; ++b) {
+            if (use_tc) {
+                BK(tc_fwd(zlat, false, pair_z[b], m.b_z[b], x, true, R));
+                BK(cudaMemcpyAsync(xa[b], x, (size_t)R * Hd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                BK(tc_fwd(x, true, pair_0[b], m.b_fc0[b], net[b], false, R));
+                BK(tc_fwd(net[b], true, pair_1[b], m.b_fc1[b], x, true, R));
+                continue;
+            }
             BK((linear<false, true>(zlat, L, m.w_z[b], L, m.b_z[b], x, Hd, R, L, Hd, st)));
             BK(cudaMemcpyAsync(xa[b], x, (size_t)R * Hd * sizeof(float), cudaMemcpyDeviceToDevice, st));
             BK((linear<true, false>(x, Hd, m.w_fc0[b], Hd, m.b_fc0[b], net[b], Hd, R, Hd, Hd, st)));
@@ -303,6 +411,11 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         for (int b = 0; b < n_post; ++b) {
             const int B = n_pre + b;
             BK(cudaMemcpyAsync(xci[b], xc, (size_t)ns * Hd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (use_tc) {
+                BK(tc_fwd(xc, true, pair_0[B], m.b_fc0[B], netc[b], false, ns));
+                BK(tc_fwd(netc[b], true, pair_1[B], m.b_fc1[B], xc, true, ns));
+                continue;
+            }
             BK((linear<true, false>(xc, Hd, m.w_fc0[B], Hd, m.b_fc0[B], netc[b], Hd, ns, Hd, Hd, st)));
             BK((linear<true, true>(netc[b], Hd, m.w_fc1[B], Hd, m.b_fc1[B], xc, Hd, ns, Hd, Hd, st)));
         }
@@ -316,6 +429,15 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         for (int b = n_post - 1; b >= 0; --b) {
             const int B = n_pre + b;
             // x_out = x_in + fc_1(relu(net)),  net = fc_0(relu(x_in));  gxc = dL/dx_out
+            if (use_tc) {
+                BK(tc_pack_act(netc[b], true, ns, AP));
+                BK(tc_wgrad(gxc, map_ap, ns, g_w1[B], g_b1[B]));
+                BK(tc_dgrad(gxc, 2 * B + 1, netc[b], gnetc, false, ns));                    // gnetc = (gxc W1) * (net > 0)
+                BK(tc_pack_act(xci[b], true, ns, AP));
+                BK(tc_wgrad(gnetc, map_ap, ns, g_w0[B], g_b0[B]));
+                BK(tc_dgrad(gnetc, 2 * B, xci[b], gxc, true, ns));                           // gxc += (gnetc W0) * (x_in > 0)
+                continue;
+            }
             BK((wgrad<true>(gxc, Hd, netc[b], Hd, ns, Hd, Hd, g_w1[B], g_b1[B], st)));
             BK((linear<false, false>(gxc, Hd, wT1[B], Hd, nullptr, gnetc, Hd, ns, Hd, Hd, st)));
             relu_mask_kernel<<<grid1d(ns * Hd), 256, 0, st>>>(gnetc, netc[b], ns * Hd);
@@ -330,6 +452,18 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         BK(cudaMemsetAsync(gz, 0, (size_t)R * L * sizeof(float), st));
         for (int b = n_pre - 1; b >= 0; --b) {
             // x_out = xa + fc_1(relu(net)),  net = fc_0(relu(xa)),  xa = x_prev + lin_z[b](zlat);  gx = dL/dx_out
+            if (use_tc) {
+                if (b == n_pre - 1) BK(tc_pack_act(zlat, false, R, ZP));                     // shared by the lin_z weight gradients of all blocks
+                BK(tc_pack_act(net[b], true, R, AP));
+                BK(tc_wgrad(gx, map_ap, R, g_w1[b], g_b1[b]));
+                BK(tc_dgrad(gx, 2 * b + 1, net[b], gnet, false, R));                         // gnet = (gx W1) * (net > 0)
+                BK(tc_pack_act(xa[b], true, R, AP));
+                BK(tc_wgrad(gnet, map_ap, R, g_w0[b], g_b0[b]));
+                BK(tc_dgrad(gnet, 2 * b, xa[b], gx, true, R));                               // gx += (gnet W0) * (xa > 0)  = dL/dxa
+                BK(tc_wgrad(gx, map_zp, R, g_wz[b], g_bz[b]));
+                BK(tc_dgrad(gx, 2 * m.n_blocks + b, nullptr, gz, true, R));                  // gz += gx W_z
+                continue;
+            }
             BK((wgrad<true>(gx, Hd, net[b], Hd, R, Hd, Hd, g_w1[b], g_b1[b], st)));
             BK((linear<false, false>(gx, Hd, wT1[b], Hd, nullptr, gnet, Hd, R, Hd, Hd, st)));
             relu_mask_kernel<<<grid1d(R * Hd), 256, 0, st>>>(gnet, net[b], R * Hd);

@@ -50,7 +50,8 @@ struct diner_ctx {
     DevBuf mlp_store;                // all fp32 parameters, contiguous
     SceneDev scene{};
     DevBuf latent, maps, cams;       // library-owned scene copies
-    DevBuf zbuf, netbuf, simt_ws, rays_dev, out_dev, rays_img, bwd_ws, dpre;
+    DevBuf zbuf, netbuf, simt_ws, rays_dev, out_dev, rays_img, bwd_ws, bwd_tc, dpre;
+    int backward_tc = 1;             // training-step backward: 1 = tcgen05 GEMMs for the 512-wide layers (gemm_tc3.cu), 0 = fp32 CUDA cores
     void* host_pin = nullptr; size_t host_pin_cap = 0;
     TcState tc;                      // packed weights + scratch of the tcgen05 path
     long long launches = 0;
@@ -93,7 +94,7 @@ extern "C" void diner_destroy(diner_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     c->mlp_store.release(); c->latent.release(); c->maps.release(); c->cams.release();
-    c->zbuf.release(); c->netbuf.release(); c->simt_ws.release(); c->rays_dev.release(); c->out_dev.release(); c->rays_img.release(); c->bwd_ws.release(); c->dpre.release();
+    c->zbuf.release(); c->netbuf.release(); c->simt_ws.release(); c->rays_dev.release(); c->out_dev.release(); c->rays_img.release(); c->bwd_ws.release(); c->bwd_tc.release(); c->dpre.release();
     tc_release(c->tc);
     if (c->host_pin) cudaFreeHost(c->host_pin);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -421,21 +422,26 @@ extern "C" int diner_render_backward(diner_ctx* c, const float* rays, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const long long l0 = g_launches;
     const long long n_rays = (long long)SB * NR, n = n_rays * K;
-    // fp32 forward for the per-sample outputs the compositing derivative needs
+    // forward for the per-sample outputs the compositing derivative needs: the fused tcgen05 kernel when the backward runs on
+    // the tensor cores (same arithmetic as the training forward), else fp32 CUDA cores
     CUDA_TRY(c->netbuf.reserve((size_t)n * 4 * sizeof(float)));
     QueryArgs q{};
     q.SB = SB; q.n_per_sb = (long long)NR * K; q.rays = rays; q.z = z; q.K = K;
     q.out = c->netbuf.as<float>();
-    rc = run_query(c, q, DINER_MODE_FP32, st);
+    const bool tcb = c->backward_tc && c->tc.ready && c->mlp.d_hidden == 512 && c->mlp.d_latent == 512 && c->softplus_beta == 0.0f &&
+                     c->scene.NV <= 32;
+    rc = run_query(c, q, tcb ? DINER_MODE_PARITY : DINER_MODE_FP32, st);
     if (rc) return rc;
     CUDA_TRY(c->dpre.reserve((size_t)n * 4 * sizeof(float)));
     CUDA_TRY(launch_composite_backward(rays, z, q.out, n_rays, K, white_bkgd, g_rgb, g_depth, c->dpre.as<float>(), st));
     const long long chunk = 32768;
     CUDA_TRY(c->bwd_ws.reserve(backward_workspace_bytes(c->mlp, c->scene, chunk)));
-    cudaError_t e = backward_simt(c->scene, c->mlp, q, c->dpre.as<float>(), grad_params, d_latent, c->bwd_ws.as<float>(), chunk, st);
+    if (tcb) CUDA_TRY(c->bwd_tc.reserve(backward_tc_workspace_bytes(c->mlp, c->scene, chunk)));
+    cudaError_t e = backward_simt(c->scene, c->mlp, q, c->dpre.as<float>(), grad_params, d_latent, c->bwd_ws.as<float>(), chunk, st,
+                                  tcb ? &c->tc : nullptr, tcb ? c->bwd_tc.as<uint8_t>() : nullptr, c->num_sms);
     c->launches += g_launches - l0;
     if (e == cudaErrorNotSupported) return fail(DINER_E_UNSUPPORTED, "backward needs >= 1 block before and after combine_layer");
-    if (e != cudaSuccess) return fail(DINER_E_CUDA, "backward_simt: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(DINER_E_CUDA, "backward: %s (watchdog code %d)", cudaGetErrorString(e), c->tc.err_flag ? *c->tc.err_flag : -1);
     return DINER_OK;
 }
 
@@ -500,7 +506,10 @@ extern "C" int diner_render_host(diner_ctx* c, const float* rays_host, int SB, i
 
 extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) {
     if (!c || !key) return fail(DINER_E_INVALID, "NULL ctx / key");
-    if (!strcmp(key, "fused")) {
+    if (!strcmp(key, "backward_tc")) {
+        if (value != 0 && value != 1) return fail(DINER_E_INVALID, "backward_tc must be 0 or 1");
+        c->backward_tc = (int)value;
+    } else if (!strcmp(key, "fused")) {
         if (value != 0 && value != 1) return fail(DINER_E_INVALID, "fused must be 0 or 1");
         c->tc.fused = (int)value;
     } else if (!strcmp(key, "post_tiles")) {

@@ -56,8 +56,11 @@ size_t simt_workspace_bytes(const MlpDev& m, long long rows);
 // --- backward pass, fp32 CUDA cores (backward_simt.cu; experimental) ------------------------------------------------------
 size_t backward_param_count(const MlpDev& m);
 size_t backward_workspace_bytes(const MlpDev& m, const SceneDev& s, long long chunk_samples);
+struct TcState;
+size_t backward_tc_workspace_bytes(const MlpDev& m, const SceneDev& s, long long chunk_samples);
 cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q, const float* d_pre, float* grad_params,
-                          float* d_latent, float* ws, long long chunk, cudaStream_t st);
+                          float* d_latent, float* ws, long long chunk, cudaStream_t st, TcState* tcs = nullptr, uint8_t* tcws = nullptr,
+                          int num_sms = 148);
 cudaError_t launch_composite_backward(const float* rays, const float* z, const float* net_out, long long n_rays, int K, int white,
                                       const float* g_rgb, const float* g_depth, float* d_pre, cudaStream_t st);
 

@@ -1,0 +1,452 @@
+// Generic tcgen05 GEMM of the training-step backward (BASELINE config 3):
+//
+//     C[rows x 512] (=, +=, atomic +=)  epilogue( act(A[rows x K]) . Bp[512 x K]^T )
+//
+// A: fp32 row-major in global memory (K contiguous), split on the fly into fp16 hi/lo K-major SWIZZLE_128B operand tiles;
+// Bp: fp16 hi/lo tiles already packed in UMMA order (tc::pack_weight_kernel for weights, pack_rows_kernel for activations),
+//     streamed by 2-SM TMA; C: fp32 row-major.  Same arithmetic as the forward parity mode (mlp_tc.cu): three MMAs per product,
+//     fp32 accumulation in TMEM.  One kernel serves the three GEMM flavours of the backward (backward_simt.cu walks the chain):
+//       forward recompute / data gradient :  rows = sample(-view) rows, K = 512, Bp = packed W or packed W^T
+//       weight gradient                   :  rows = the 512 outputs (A = G^T), K = sample rows (split over the CTA pairs),
+//                                            Bp = packed relu(activations)^T, C = dW accumulated with atomics
+// Unlike the forward MLP kernel there is no dependent epilogue inside a work item, so this is a plain pipelined GEMM:
+//   warps 0,2,3 : TMA producers of the Bp ring (6 x 16 KiB)        warp 1 (leader CTA): MMA issuer (cta_group::2, M=128, N=256)
+//   warps 4..11 : A loaders (fp32 -> fp16 hi/lo), two buffers of 4 K blocks each
+//   warps 12..15: epilogue (TMEM -> registers -> global), on the other one of two 256-column accumulators
+#include "mlp_tc.h"
+
+namespace tc3 {
+
+using namespace tc;
+using tc2::act_off;
+using tc2::map_to_cta;
+using tc2::mbar_arrive_remote;
+using tc2::umma2_f16;
+using tc2::umma2_commit_pair;
+using tc2::make_idesc2;
+
+constexpr int ROWS = 64;                          // rows per CTA (128 per pair)
+constexpr int NUM_THREADS = 512;
+constexpr int NST = 6;                            // Bp ring stages
+constexpr int GK = 4;                             // K blocks per A buffer
+constexpr int ACT_KB_BYTES = ROWS * 128;          // 8 KiB per K block and copy
+constexpr int ABUF_BYTES = 2 * GK * ACT_KB_BYTES; // hi + lo of one A buffer: 64 KiB
+constexpr int OFF_A = NST * WTILE_BYTES;
+constexpr int OFF_BARS = OFF_A + 2 * ABUF_BYTES;
+constexpr int SMEM_BYTES = OFF_BARS + 256;
+constexpr int NUM_LOADER_WARPS = 8, NUM_EPI_WARPS = 4, LOADER_WARP0 = 4, EPI_WARP0 = 12;
+
+struct Args {
+    CUtensorMap bmap;          // packed Bp stream as rows of 128 B; box = one 16 KiB tile
+    const float* A;            // (rows, lda) fp32
+    long long lda, rows;
+    long long K;               // valid K (k >= K reads as zero); the packed Bp is zero-padded to nkb_total * 64
+    int nkb_total;             // K blocks of the packed Bp per 128-row tile (tile index stride)
+    int relu_a;                // max(a, 0) while loading A
+    const float* a_scale;      // device {s, 1/s} or nullptr: A is multiplied by the power of two s before the fp16 split and the
+                               // accumulator by 1/s (gradient operands are far below fp16's normal range: loss-scaling per call)
+    long long b_pair0;         // first (hi, lo) tile pair of Bp in the stream
+    int n_slices;              // split-K: work item = (row tile, K slice); slices of kb_per_slice K blocks
+    int kb_per_slice;
+    float* C;                  // (rows, ldc)
+    long long ldc;
+    int mode;                  // 0 store, 1 C += (plain read-modify-write: one item per C tile), 2 atomicAdd (split-K)
+    float scale;               // applied to the accumulator (W_INV for W_SCALE-packed weights, 1 for packed activations)
+    const float* bias;         // + bias[n] or nullptr
+    const float* mask;         // * (mask[row][n] > 0) or nullptr   (ldm)
+    const float* add;          // + add[row][n] or nullptr          (ldd)
+    long long ldm, ldd;
+    int* err;
+};
+
+__device__ __forceinline__ void st_c(const Args& a, long long row, int n0, const uint32_t* v) {
+    // 32 consecutive outputs of one row
+    float o[32];
+    const float sc = a.a_scale ? a.scale * __ldg(a.a_scale + 1) : a.scale;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]) * sc;
+    if (a.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg((const float4*)(a.bias + n0 + i));
+            o[i] += b.x; o[i + 1] += b.y; o[i + 2] += b.z; o[i + 3] += b.w;
+        }
+    }
+    if (a.mask) {
+        const float4* m = (const float4*)(a.mask + row * a.ldm + n0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = m[i >> 2];
+            o[i] = b.x > 0.0f ? o[i] : 0.0f; o[i + 1] = b.y > 0.0f ? o[i + 1] : 0.0f;
+            o[i + 2] = b.z > 0.0f ? o[i + 2] : 0.0f; o[i + 3] = b.w > 0.0f ? o[i + 3] : 0.0f;
+        }
+    }
+    if (a.add) {
+        const float4* m = (const float4*)(a.add + row * a.ldd + n0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = m[i >> 2];
+            o[i] += b.x; o[i + 1] += b.y; o[i + 2] += b.z; o[i + 3] += b.w;
+        }
+    }
+    float* c = a.C + row * a.ldc + n0;
+    if (a.mode == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(c + i, o[i]);
+    } else {
+        float4* c4 = (float4*)c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 r = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+            if (a.mode == 1) { const float4 p = c4[i >> 2]; r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
+            c4[i >> 2] = r;
+        }
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ Args a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool is_leader_cta = crank == 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_base + OFF_BARS;            // NST: Bp stage landed (leader's barrier collects both CTAs' copies)
+    const uint32_t bar_empty = bar_full + 8 * NST;             // NST: stage free (pair commit)
+    const uint32_t bar_afull = bar_empty + 8 * NST;            // 2: (leader) A buffer of both CTAs ready
+    const uint32_t bar_aempty = bar_afull + 16;                // 2: A buffer no longer read (pair commit)
+    const uint32_t bar_accfull = bar_aempty + 16;              // 2: accumulator complete (pair commit)
+    const uint32_t bar_accempty = bar_accfull + 16;            // 2: (leader) accumulator read out by both CTAs' epilogue warps
+    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + OFF_BARS + 8 * (2 * NST + 8));
+
+    if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 91); __trap(); }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_afull + 8 * i, NUM_LOADER_WARPS + 1);
+            mbar_init(bar_aempty + 8 * i, 1);
+            mbar_init(bar_accfull + 8 * i, 1);
+            mbar_init(bar_accempty + 8 * i, NUM_EPI_WARPS + 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // work items: (row tile of 128 rows over the pair, K slice); every role walks the same list
+    const long long n_row_tiles = (a.rows + 2 * ROWS - 1) / (2 * ROWS);
+    const long long n_items = n_row_tiles * a.n_slices;
+    const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const long long kb_all = (a.K + KBLK - 1) / KBLK;
+    auto item_kb = [&](long long item, int& kb0, int& kb1) {
+        const int sl = (int)(item / n_row_tiles);
+        kb0 = sl * a.kb_per_slice;
+        const long long e = (long long)kb0 + a.kb_per_slice;
+        kb1 = (int)(e < kb_all ? e : kb_all);
+        if (kb1 < kb0) kb1 = kb0;
+    };
+
+    const int prod_idx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+    if (prod_idx >= 0) {
+        // ===== Bp producers: ring use u of an item = (kb, n2, hi|lo); this CTA loads the 128-row tile (2*n2 + rank)
+        const bool leader = elect_one();
+        const uint32_t leader_full = map_to_cta(bar_full, 0);
+        long long use = 0;
+        for (long long item = pair; item < n_items; item += n_pairs) {
+            int kb0, kb1;
+            item_kb(item, kb0, kb1);
+            const long long uses = (long long)(kb1 - kb0) * 4;
+            for (long long u = 0; u < uses; ++u, ++use) {
+                const int st = (int)(use % NST);
+                if (st % 3 != prod_idx) continue;
+                const uint32_t ph = (uint32_t)((use / NST) & 1);
+                mbar_wait(bar_empty + 8 * st, ph ^ 1, a.err, 110);
+                if (leader) {
+                    const int kb = kb0 + (int)(u >> 2), n2 = (int)(u >> 1) & 1, hl = (int)u & 1;
+                    const long long tix = 2 * (a.b_pair0 + (long long)(2 * n2 + (int)crank) * a.nkb_total + kb) + hl;
+                    if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, 2 * WTILE_BYTES);
+                    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(smem_base + st * WTILE_BYTES), "l"(&a.bmap), "r"(0), "r"((int)(tix * 128)), "r"(leader_full + 8 * st) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1 && is_leader_cta) {
+        // ===== MMA issuer
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc2(256);
+        long long use = 0, grp = 0, it = 0;
+        for (long long item = pair; item < n_items; item += n_pairs, ++it) {
+            int kb0, kb1;
+            item_kb(item, kb0, kb1);
+            const int acc = (int)(it & 1);
+            mbar_wait(bar_accempty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1), a.err, 120);       // epilogue of item it-2 has read it
+            tc_fence_after();
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int kl = (kb - kb0) % GK;
+                const int buf = (int)(grp & 1);
+                if (kl == 0) {
+                    mbar_wait(bar_afull + 8 * buf, (uint32_t)((grp >> 1) & 1), a.err, 121);
+                    tc_fence_after();
+                }
+                for (int n2 = 0; n2 < 2; ++n2) {
+                    const uint32_t d = tmem + (uint32_t)(256 * acc + 128 * n2);
+                    for (int hl = 0; hl < 2; ++hl, ++use) {
+                        const uint32_t st = (uint32_t)(use % NST), ph = (uint32_t)((use / NST) & 1);
+                        mbar_wait(bar_full + 8 * st, ph, a.err, 122);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint64_t bdesc = make_desc(smem_base + st * WTILE_BYTES, 16, 1024);
+                            const uint64_t ahi = make_desc(smem_base + OFF_A + buf * ABUF_BYTES + kl * ACT_KB_BYTES, 16, 1024);
+                            const uint64_t alo = make_desc(smem_base + OFF_A + buf * ABUF_BYTES + (GK + kl) * ACT_KB_BYTES, 16, 1024);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                umma2_f16(d, ahi + 2 * j, bdesc + 2 * j, idesc, (hl | (kb - kb0) | j) ? 1u : 0u);
+                                if (hl == 0) umma2_f16(d, alo + 2 * j, bdesc + 2 * j, idesc, 1u);      // A_lo * B_hi rides on the hi tile
+                            }
+                            umma2_commit_pair(bar_empty + 8 * st);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (kl == GK - 1 || kb + 1 == kb1) {
+                    if (leader) umma2_commit_pair(bar_aempty + 8 * buf);
+                    __syncwarp();
+                    ++grp;
+                }
+            }
+            if (kb1 == kb0) {                                        // empty slice: nothing was accumulated (not reached with sane slicing)
+            }
+            if (leader) umma2_commit_pair(bar_accfull + 8 * acc);
+            __syncwarp();
+        }
+    } else if (warp >= LOADER_WARP0 && warp < EPI_WARP0) {
+        // ===== A loaders: 64 rows x (GK x 64) k of fp32 -> fp16 hi/lo chunks, one (row, 8-k chunk) at a time
+        const int lw = warp - LOADER_WARP0, lt = threadIdx.x - LOADER_WARP0 * 32;
+        const float asc = a.a_scale ? __ldg(a.a_scale) : 1.0f;
+        const uint32_t leader_afull = map_to_cta(bar_afull, 0);
+        long long grp = 0;
+        for (long long item = pair; item < n_items; item += n_pairs) {
+            int kb0, kb1;
+            item_kb(item, kb0, kb1);
+            const long long row0 = ((item % n_row_tiles) * 2 + crank) * ROWS;
+            for (int g0 = kb0; g0 < kb1; g0 += GK, ++grp) {
+                const int buf = (int)(grp & 1), nk = (kb1 - g0 < GK ? kb1 - g0 : GK);
+                uint8_t* Ahi = smem + OFF_A + buf * ABUF_BYTES;
+                uint8_t* Alo = Ahi + GK * ACT_KB_BYTES;
+                mbar_wait(bar_aempty + 8 * buf, (uint32_t)(((grp >> 1) & 1) ^ 1), a.err, 130);
+                const int chunks = ROWS * nk * 8;                    // 16-byte chunks of this group
+                for (int c = lt; c < chunks; c += NUM_LOADER_WARPS * 32) {
+                    const int r = c / (nk * 8), kc = c % (nk * 8);
+                    long long row = row0 + r;
+                    if (row >= a.rows) row = a.rows - 1;
+                    const long long k = (long long)g0 * KBLK + 8 * kc;
+                    float x[8];
+                    if (k + 8 <= a.K) {
+                        const float4 f0 = __ldg((const float4*)(a.A + row * a.lda + k)), f1 = __ldg((const float4*)(a.A + row * a.lda + k + 4));
+                        x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w; x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[i] = k + i < a.K ? __ldg(a.A + row * a.lda + k + i) : 0.0f;
+                    }
+                    if (a.relu_a) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.0f);
+                    }
+                    if (a.a_scale) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[i] *= asc;
+                    }
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    const uint32_t off = act_off(r, kc);
+                    *(uint4*)(Ahi + off) = hi;
+                    *(uint4*)(Alo + off) = lo;
+                }
+                fence_proxy_async();
+                if (is_leader_cta) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_afull + 8 * buf);
+                } else if (lw == 0) {
+                    // peer CTA: join the loader warps on a named barrier and send ONE remote arrive.  One barrier id per A buffer: a
+                    // fast warp may be one group ahead of warp 0 (the other buffer), never two (that needs this group consumed)
+                    if (buf == 0) asm volatile("bar.sync 2, %0;" ::"n"(NUM_LOADER_WARPS * 32) : "memory");
+                    else asm volatile("bar.sync 4, %0;" ::"n"(NUM_LOADER_WARPS * 32) : "memory");
+                    if (lane == 0) mbar_arrive_remote(leader_afull + 8 * buf);
+                } else {
+                    if (buf == 0) asm volatile("bar.arrive 2, %0;" ::"n"(NUM_LOADER_WARPS * 32) : "memory");
+                    else asm volatile("bar.arrive 4, %0;" ::"n"(NUM_LOADER_WARPS * 32) : "memory");
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue: TMEM lanes 32q..32q+31 = rows 32*(q&1)+lane, hidden half (q>>1) of each N tile
+        const int q = warp & 3, ew = warp - EPI_WARP0;
+        const int r = 32 * (q & 1) + lane;
+        const uint32_t leader_accempty = map_to_cta(bar_accempty, 0);
+        long long it = 0;
+        for (long long item = pair; item < n_items; item += n_pairs, ++it) {
+            const int acc = (int)(it & 1);
+            const long long row = ((item % n_row_tiles) * 2 + crank) * ROWS + r;
+            mbar_wait(bar_accfull + 8 * acc, (uint32_t)((it >> 1) & 1), a.err, 140);
+            tc_fence_after();
+#pragma unroll 1
+            for (int n2 = 0; n2 < 2; ++n2) {
+#pragma unroll 1
+                for (int c32 = 0; c32 < 4; ++c32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 * acc + 128 * n2 + 32 * c32), v);
+                    if (row < a.rows) st_c(a, row, 256 * n2 + 128 * (q >> 1) + 32 * c32, v);
+                }
+            }
+            tc_fence_before();
+            if (is_leader_cta) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
+            } else if (ew == 0) {                                    // (one named barrier id per accumulator, like the loaders' per buffer)
+                if (acc == 0) asm volatile("bar.sync 3, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+                else asm volatile("bar.sync 5, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+                if (lane == 0) mbar_arrive_remote(leader_accempty + 8 * acc);
+            } else {
+                if (acc == 0) asm volatile("bar.arrive 3, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+                else asm volatile("bar.arrive 5, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// Activations (R, ld) fp32 -> Bp tiles of act(X)^T: "weight" matrix with out = n_cols (512) and in = R, i.e. tile (m, kb) holds
+// columns 128 m .. +128 of rows 64 kb .. +64 as [128 rows = columns of X][64 k = rows of X], fp16 hi/lo, UMMA K-major SWIZZLE_128B
+// order.  One CTA per tile pair; the transposition goes through shared memory so that both the reads (along the columns of X)
+// and the 16 KiB tile writes are coalesced.  Rows >= R are zero (K padding).
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ X, long long ld, long long R, int nkb, int relu,
+                                                        uint8_t* __restrict__ dst) {
+    __shared__ float tile[64][129];
+    const int m = blockIdx.x / nkb, kb = blockIdx.x % nkb;
+    for (int i = threadIdx.x; i < 64 * 128; i += 256) {
+        const int k = i >> 7, c = i & 127;
+        const long long row = (long long)kb * 64 + k;
+        float v = row < R ? X[row * ld + 128 * m + c] : 0.0f;
+        if (relu) v = fmaxf(v, 0.0f);
+        tile[k][c] = v;
+    }
+    __syncthreads();
+    uint8_t* hi = dst + (size_t)blockIdx.x * 2 * WTILE_BYTES;
+    uint8_t* lo = hi + WTILE_BYTES;
+    for (int i = threadIdx.x; i < 128 * 8; i += 256) {          // (tile row r = column of X, 8-k chunk)
+        const int r = i >> 3, kc = i & 7;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = tile[8 * kc + j][r];
+        uint4 h, l;
+        split8(x, h, l);
+        const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((kc ^ (r & 7)) << 4);
+        *(uint4*)(hi + off) = h;
+        *(uint4*)(lo + off) = l;
+    }
+}
+
+// (rows, cols) -> (cols, ld_dst) with ld_dst >= rows (a multiple of 64 so that the GEMM's 16-byte loads stay aligned)
+__global__ void transpose_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int cols, long long ld_dst) {
+    __shared__ float tile[32][33];
+    const long long r0 = (long long)blockIdx.y * 32;
+    const int c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const long long r = r0 + i;
+        const int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[r * cols + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i;
+        const long long r = r0 + threadIdx.x;
+        if (c < cols && r < ld_dst) dst[(long long)c * ld_dst + r] = tile[threadIdx.x][i];
+    }
+}
+
+// loss-scaling of the gradient operands: amax[0] = max |x| (float bits, atomicMax on the non-negative pattern), then
+// scale = {s, 1/s} with s = the power of two that brings the maximum to ~2^11
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ amax) {
+    float m = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f && m < 3.0e38f) atomicMax(amax, __float_as_uint(m));
+}
+__global__ void make_scale_kernel(const unsigned int* __restrict__ amax, float* __restrict__ scale) {
+    const float m = __uint_as_float(*amax);
+    float s = 1.0f;
+    if (m > 0.0f) {
+        int e;
+        frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+        int k = 11 - e;
+        k = k > 100 ? 100 : (k < -100 ? -100 : k);
+        s = ldexpf(1.0f, k);
+    }
+    scale[0] = s;
+    scale[1] = 1.0f / s;
+}
+
+// column sums: db[n] += sum_r G[r][n]   (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ G, long long ld, long long R, int n_cols, long long rows_per_cta,
+                                                     float* __restrict__ db) {
+    const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = r0 + rows_per_cta < R ? r0 + rows_per_cta : R;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_cols) return;
+    float s = 0.0f;
+    for (long long r = r0; r < r1; ++r) s += G[r * ld + c];
+    atomicAdd(db + c, s);
+}
+
+}  // namespace tc3
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+struct Tc3Map { CUtensorMap map; const void* base = nullptr; size_t bytes = 0; };
+
+static cudaError_t tc3_make_map(Tc3Map& m, const void* base, size_t bytes) {
+    if (m.base == base && m.bytes == bytes) return cudaSuccess;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {64, (cuuint64_t)(bytes / 128)};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = ((EncodeFn)fn)(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
+    m.base = base; m.bytes = bytes;
+    return cudaSuccess;
+}
+
+// C (rows x 512) op= epilogue(act(A (rows x K)) . Bp^T); see tc3::Args.  grid_pairs = CTA pairs to launch (<= resident pairs).
+static cudaError_t tc3_gemm(tc3::Args a, int grid_pairs, int* err_flag, cudaStream_t st) {
+    using namespace tc3;
+    if (a.rows <= 0 || a.K <= 0) return cudaSuccess;
+    auto kern = gemm_kernel;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    a.err = err_flag;
+    const long long n_items = ((a.rows + 2 * ROWS - 1) / (2 * ROWS)) * a.n_slices;
+    long long g = n_items < grid_pairs ? n_items : grid_pairs;
+    if (g < 1) g = 1;
+    g_launches++;
+    kern<<<(unsigned)(2 * g), NUM_THREADS, SMEM_BYTES, st>>>(a);
+    return cudaGetLastError();
+}
