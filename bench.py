@@ -196,7 +196,8 @@ def train_bench(args):
     """BASELINE.json configs[2] (NOT part of the driver contract): Facescape-shaped
     training step -- SB=4 scenes of 256x256, 4 source views, 128 samples/ray, 4096 random rays per scene (ray_batch_size,
     diner.py:57), MSE loss, backward through the renderer to the ResnetFC parameters and the latent maps, Adam step
-    (diner.py:333).  Forward in --mode, backward on fp32 CUDA cores (csrc/backward_simt.cu).  Single GPU."""
+    (diner.py:333).  Forward in --mode; backward through diner_render_backward (tcgen05 GEMMs of csrc/gemm_tc3.cu for the 512-wide
+    layers; DINER_B200_BACKWARD_TC=0 selects the fp32 CUDA-core path).  Single GPU."""
     from diner_b200 import synthetic as S
     from diner_b200.nerf_renderer import NeRFRendererDGS
     from diner_b200.predict import calc_losses
@@ -238,7 +239,9 @@ def train_bench(args):
     flop = 3 * rays_step * Kt * (4774912 * NVt + 2101248)          # forward + ~2x for dgrad + wgrad
     print(json.dumps({"metric": "train_rays_per_sec", "value": rays_step / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                      "dtype": "forward %s, backward f32 CUDA cores (experimental)" % args.mode, "data": "synthetic",
+                      "dtype": ("forward %s (fused tcgen05 kernel), backward: tcgen05 GEMMs (f16x3 operands, f32 accumulate) for the 512-wide layers"
+                                if os.environ.get("DINER_B200_BACKWARD_TC", "1") != "0" else "forward %s, backward f32 CUDA cores") % args.mode,
+                      "data": "synthetic",
                       "config": {"workload": "Facescape-shaped synthetic training step: SB=4 x 256x256, 4 src views, 128 samples/ray, "
                                              "4096 rays/scene, MSE + backward + Adam", "mode": args.mode},
                       "loss": float(loss), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12}))
@@ -403,7 +406,7 @@ def main():
         passes = 3 if args.mode == "parity" else 1
         exec_per_sample = NV * (2 * 64 * 512 + 6 * 2 * 512 * 512) + (4 * 2 * 512 * 512 + 2 * 512 * 32 if fused else 0)
         executed = passes * exec_per_sample * n_samp_rank / n_pre_launches / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
-        tr = latest_traffic() if args.mode == "parity" else None
+        tr = latest_traffic() if (args.mode == "parity" and args.workload == "dtu512") else None   # captured on this workload's shape
         e2e_d2h = (rgb_h.numel() + dep_h.numel()) * 4 if world == 1 else img_h.numel() * 4
         line = {
             "metric": "rays_per_sec", "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
