@@ -238,11 +238,9 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
 cudaError_t launch_sampler(const SceneDev& s, const SamplerArgs& a, int num_sms, cudaStream_t st) {
     const int Cpad = (a.C + 31) & ~31;
     const size_t smem = (size_t)WARPS_PER_CTA * (2 * Cpad + 2 * a.K) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {     // per launch: the attribute is per device and one process may drive several (a few hundred ns)
         cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const long long total = (long long)a.SB * a.NR;
     long long want = (total + WARPS_PER_CTA - 1) / WARPS_PER_CTA;

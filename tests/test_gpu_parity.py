@@ -659,3 +659,56 @@ def test_cam_sweep_loop_and_output_side(tmp_path):
     w = IO.ImageWriter()
     IO.write_prediction_images(w, str(tmp_path), ["s0"], rgb, depth, b["src_rgbs"], b["target_rgb"])
     assert len(w.close()) == 4
+
+
+def test_edge_geometry_vs_oracle():
+    """Geometry the fixtures do not reach (Appendix A of SURVEY.md: no guard for p.z <= 0, border / zeros padding, exponential std
+    padding far outside the image): rays from a target camera placed BETWEEN the source cameras and the object and from one looking
+    away, so samples project behind source cameras, far outside their images and onto the padding rings; odd sizes (K = 17, C = 77,
+    G = 5, 3 views).  Sampler and render vs the oracle on cuda on every ray, query / compositing vs the CPU oracle stage-wise."""
+    from diner_b200 import synthetic as S
+    cfg = dict(H=40, W=56, NV=3, SB=1, near=0.2, far=3.5, K=17, C=77, G=5, white=False, nr=8, seed=44)
+    batch, latent, mlp, _, _ = MG.case_inputs(cfg)
+    H, W = cfg["H"], cfg["W"]
+    E = batch["target_extrinsics"].clone()                       # (1,4,4) world->cam
+    E2 = E.clone()
+    E2[0, :3, 3] += torch.tensor([0.35, -0.2, -1.1])             # moved forward / sideways: the volume straddles the source cameras
+    E3 = E.clone()                                               # same camera centre, turned by 180 degrees: looking away from the object
+    centre = -E[0, :3, :3].T @ E[0, :3, 3]
+    E3[0, :3, :3] = torch.diag(torch.tensor([-1.0, 1.0, -1.0])) @ E[0, :3, :3]
+    E3[0, :3, 3] = -E3[0, :3, :3] @ centre
+    rays = torch.cat([S.gen_rays(e, batch["target_intrinsics"], W, H, torch.full((1,), cfg["near"]), torch.full((1,), cfg["far"])).view(1, H * W, 8)
+                      [:, (torch.arange(160) * 13) % (H * W)] for e in (E2, E3)], dim=1).contiguous()
+    NR = rays.shape[1]
+    noise = dict(u_coarse=S.hash_uniform((1, NR, cfg["C"]), 44, 901), g_noise=S.hash_normal((1, NR, cfg["G"]), 44, 902),
+                 u_fill=S.hash_uniform((1, NR, cfg["K"]), 44, 903))
+    scene = O.make_scene_state(batch, latent, mlp)
+    sc = oracle_scene_on(scene, "cuda")
+    nz = {k: v.cuda().contiguous() for k, v in noise.items()}
+    with torch.no_grad():
+        zc = O.fill_up_uniform(O.sample_depthguided(sc, rays.cuda(), cfg["K"], cfg["C"], cfg["G"], nz["u_coarse"], nz["g_noise"]), rays.cuda(), nz["u_fill"])
+        w_c, rgb_c, dep_c = O.composite(sc, rays.cuda(), zc, cfg["white"])
+        w_o, rgb_o, dep_o = O.composite(scene, rays, zc.cpu(), cfg["white"])
+    # how much of the edge behaviour the case really exercises (computed with the oracle's own projection)
+    xyz = (rays[..., None, :3] + zc.cpu().unsqueeze(-1) * rays[..., None, 3:6]).reshape(1, -1, 3)
+    xc = O.world_to_cam(scene, xyz)
+    uv = O.project_uv(scene, xc)
+    behind = float((xc[..., 2] <= 0).float().mean())
+    outside = float(((uv.abs() > 1).any(-1)).float().mean())
+    print("edge geometry: %.1f %% of the sample-views behind a source camera, %.1f %% outside its image" % (100 * behind, 100 * outside))
+    assert behind > 0.02 and outside > 0.2
+    for mode, tol in (("fp32", 2e-5), ("parity", PAR_TOL)):
+        model = product_model(batch, latent, mlp, "cuda", mode)
+        ctx = model.context()
+        z = ctx.sample(rays.cuda(), cfg["K"], cfg["C"], cfg["G"], nz)
+        assert not bool(_bad((z - zc).abs().max(dim=-1).values, Z_TOL).any()), "sampler differs from the reference on cuda"
+        w, rgb, dep = ctx.composite(rays.cuda(), zc.contiguous(), cfg["white"], model.mode_id())
+        finite = torch.isfinite(rgb_o).all(-1) & torch.isfinite(dep_o)                 # the reference itself yields NaN where 0/0 projections reach the MLP
+        same_nan = (torch.isfinite(rgb.cpu()).all(-1) & torch.isfinite(dep.cpu())) == finite
+        e = ray_err(rgb.cpu()[finite], dep.cpu()[finite], rgb_o[finite], dep_o[finite])
+        print("edge geometry / %s: max |err| vs CPU oracle %.3g on %d finite rays (%d rays non-finite in the reference too)" % (
+            mode, float(e.max()) if e.numel() else 0.0, int(finite.sum()), int((~finite).sum())))
+        assert bool(same_nan.all()) and not bool(_bad(e, tol).any())
+        out = renderer_for(cfg, noise)(model, rays.cuda())
+        fin_c = torch.isfinite(rgb_c).all(-1) & torch.isfinite(dep_c)
+        assert not bool(_bad(ray_err(out.fine.rgb[fin_c], out.fine.depth[fin_c], rgb_c[fin_c], dep_c[fin_c]), TOL).any())
