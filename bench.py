@@ -326,6 +326,8 @@ def main():
     rays_host = rays.contiguous().pin_memory()          # every rank holds the ray list; it renders rays[lo:hi]
     rays_dev = rays_host.to(dev)
     ctx = model.context()
+    if os.environ.get("DINER_RAY_IMAGE_WIDTH") is None:
+        ctx.set_option("ray_image_width", W)            # the ray list is gen_rays' row-major image (every shard = whole rows of it)
 
     def packed_render(r, out, ray_offset):
         rend.render_packed(model, r, out=out, ray_offset=ray_offset)    # compositing kernel writes rgb|depth into the gather slice

@@ -105,7 +105,7 @@ class Context:
         self._check(self.lib.diner_create(ctypes.byref(h), idx))
         self.handle = h
         self._keep = []
-        for key, env in (("backward_tc", "DINER_B200_BACKWARD_TC"), ("fused", "DINER_TC_FUSED"), ("post_tiles", "DINER_TC_POST_TILES"), ("tail_kb", "DINER_TC_TAIL_KB"), ("sub_batch", "DINER_TC_SUB_BATCH"),
+        for key, env in (("ray_image_width", "DINER_RAY_IMAGE_WIDTH"), ("backward_tc", "DINER_B200_BACKWARD_TC"), ("fused", "DINER_TC_FUSED"), ("post_tiles", "DINER_TC_POST_TILES"), ("tail_kb", "DINER_TC_TAIL_KB"), ("sub_batch", "DINER_TC_SUB_BATCH"),
                          ("dbg_skip", "DINER_TC_DBG_SKIP"), ("early_split", "DINER_TC_EARLY_SPLIT")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))

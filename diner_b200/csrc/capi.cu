@@ -477,7 +477,11 @@ extern "C" int diner_render_image(diner_ctx* c, const float* target_extrinsics, 
     CUDA_TRY(c->rays_img.reserve((size_t)SB * H * W * 8 * sizeof(float)));
     rc = diner_gen_rays(c, target_extrinsics, target_intrinsics, SB, H, W, z_near, z_far, c->rays_img.as<float>(), stream);
     if (rc) return rc;
-    return diner_render(c, c->rays_img.as<float>(), SB, H * W, K, C, G, white_bkgd, mode, noise, rgb, depth, nullptr, nullptr, stream);
+    const int keep = c->tc.ray_image_w;
+    c->tc.ray_image_w = W;               // the library generated the rays itself: row-major H x W per scene -> 2-D tile order in the MLP launch
+    rc = diner_render(c, c->rays_img.as<float>(), SB, H * W, K, C, G, white_bkgd, mode, noise, rgb, depth, nullptr, nullptr, stream);
+    c->tc.ray_image_w = keep;
+    return rc;
 }
 
 extern "C" int diner_render_host(diner_ctx* c, const float* rays_host, int SB, int NR, int K, int C, int G,
@@ -512,6 +516,9 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     } else if (!strcmp(key, "fused")) {
         if (value != 0 && value != 1) return fail(DINER_E_INVALID, "fused must be 0 or 1");
         c->tc.fused = (int)value;
+    } else if (!strcmp(key, "ray_image_width")) {
+        if (value < 0 || value > (1 << 20)) return fail(DINER_E_INVALID, "ray_image_width out of range");
+        c->tc.ray_image_w = (int)value;
     } else if (!strcmp(key, "post_tiles")) {
         if (value < 1 || value > 8) return fail(DINER_E_INVALID, "post_tiles must be in [1,8]");
         c->tc.post_tiles = (int)value;

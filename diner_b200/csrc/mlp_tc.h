@@ -21,6 +21,7 @@ struct TcState {
     int table2_parity = -1, table2_tail = -1, uses2_zmap = 0, uses2_pre = 0, uses2_post = 0, max_grid2 = 0;
     int fused = 1;                // 1 = one FUSED launch per call (PRE tiles + POST tile per 64 samples, x_c in an L2-resident slab); 0 = PRE / POST launches
     int post_tiles = 1;           // FUSED: POST tiles (of 64 samples) per round = per cold start of the PRE pipeline; slab = 128 KiB x this per CTA
+    int ray_image_w = 0;          // > 0: the ray list of each scene is a row-major image of this width -> the fused launch walks it in 16 x 16 pixel tiles
     int tail_kb = 3;              // last K blocks of every full-width GEMM step issued N-tile-outer (see mlp_tc2.cu "accumulator halves")
     float* zmap = nullptr;        // pair kernel: Y_b = lin_z[b](latent) maps, [block][pixel][512] fp32 (hoisted lin_z, see mlp_tc2.cu)
     size_t zmap_bytes = 0;

@@ -135,6 +135,8 @@ struct Args {
     long long n_pix;            // ZMAP: latent pixels (SB*NV*Hl*Wl)
     int* err;
     long long* dbg_ts;          // profiling: clock64 stamps of pair 0 in round 1 ([cta][role][slot])
+    int perm_w, perm_h;         // FUSED: the rays of a scene are a row-major perm_h x perm_w image -> process them in 16 x 16 pixel tiles
+                                // (the Y-map lines gathered by neighbouring rays stay in L2); 0 = process in the caller's order
     int early_worker_kb_hi;     // next-tile Y_0 gather under the last fc_1: K blocks 1..this on the workers, the rest on the helpers
     int worker_kb_hi;           // Y_b gather inside a tile: K blocks 0..this on the workers (released before the N-outer tail), the rest on the helpers
     int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
@@ -177,6 +179,21 @@ __host__ __device__ constexpr uint32_t make_idesc2(int N) {
 // byte offset of (row r, 8-wide k chunk kc = k/8) in the K-major SWIZZLE_128B activation operand
 __device__ __forceinline__ uint32_t act_off(int r, int kc) {
     return (uint32_t)(kc >> 3) * ACT_KB_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((kc & 7) ^ (r & 7)) << 4);
+}
+
+// Processing order -> sample index.  Identity unless the caller declared the ray list a row-major image (Args::perm_w): then the
+// n-th ray processed is the n-th pixel in 16 x 16 tile order.  Only the ORDER of the work changes; every buffer keeps its layout.
+constexpr int PERM_T = 16;
+__device__ __forceinline__ long long map_sample(const Args& a, long long s) {
+    if (a.perm_w == 0) return s;
+    const long long K = a.q.K, ray = s / K, k = s - ray * K;
+    const long long img = (long long)a.perm_w * a.perm_h, sc = ray / img, i = ray - sc * img;
+    const int tiles_x = a.perm_w / PERM_T;
+    const long long tile = i / (PERM_T * PERM_T);
+    const int within = (int)(i - tile * (PERM_T * PERM_T));
+    const long long ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const long long pix = (ty * PERM_T + within / PERM_T) * a.perm_w + tx * PERM_T + within % PERM_T;
+    return (sc * img + pix) * K + k;
 }
 
 // The lo-operand region exists in both modes: the gathered fp32 Y rows are staged across (A_hi, A_lo) chunk slots in place
@@ -236,6 +253,7 @@ __device__ __noinline__ void prep_rows(const Args& a, long long tile, int wt, ui
     const int r = wt & 63, part = wt >> 6;
     long long smp = a.s_begin + tile * a.spv + r / a.NV;
     if (smp >= a.n_total) smp = a.n_total - 1;
+    smp = map_sample(a, smp);
     const int v = (r % a.NV) < a.NV_real ? (r % a.NV) : 0;          // padding views (view count not a power of two) repeat view 0
     const int sb = (int)(smp / a.q.n_per_sb);
     float px, py, pz, dx, dy, dz;
@@ -918,7 +936,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     const float4 bo = __ldg((const float4*)(bias + (size_t)(2 * n_blocks + 1) * HID));
                     const float x0 = fmaf(__uint_as_float(v[0]), W_INV, bo.x), x1 = fmaf(__uint_as_float(v[1]), W_INV, bo.y);
                     const float x2 = fmaf(__uint_as_float(v[2]), W_INV, bo.z), x3 = fmaf(__uint_as_float(v[3]), W_INV, bo.w);
-                    ((float4*)a.out)[a.s_begin + s_loc] = make_float4(1.0f / (1.0f + expf(-x0)), 1.0f / (1.0f + expf(-x1)),
+                    ((float4*)a.out)[map_sample(a, a.s_begin + s_loc)] = make_float4(1.0f / (1.0f + expf(-x0)), 1.0f / (1.0f + expf(-x1)),
                                                                      1.0f / (1.0f + expf(-x2)), fmaxf(x3, 0.0f));
                 }
             }
@@ -1171,6 +1189,15 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
         f.n_steps_post = post.n_steps; f.n_blocks_post = post.n_blocks; f.uses_post = post.uses_per_tile;
         f.tile_table_post = post.tile_table; f.bias_post = post.bias;
         f.pts = t.post_tiles > 0 ? t.post_tiles : 1;
+        // 2-D tile order of the rays when the caller declared the ray list of every scene a row-major image (diner_render_image
+        // does; diner_set_option("ray_image_width") for ray tensors): needs rays + depths (not explicit points) and whole tiles
+        if (t.ray_image_w > 0 && q.rays && q.K > 0 && (q.n_per_sb % q.K) == 0) {
+            const long long nr = q.n_per_sb / q.K;
+            if (nr % t.ray_image_w == 0 && t.ray_image_w % PERM_T == 0 && (nr / t.ray_image_w) % PERM_T == 0) {
+                f.perm_w = t.ray_image_w;
+                f.perm_h = (int)(nr / t.ray_image_w);
+            }
+        }
         f.ppr = NV * f.pts;
         f.s_begin = 0; f.n_samples = total;
         f.n_tiles = (total + (long long)ROWS * f.pts - 1) / ((long long)ROWS * f.pts);

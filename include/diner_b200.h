@@ -148,7 +148,9 @@ int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, i
 /* Tuning knobs of the tcgen05 path (not part of the reference API): key = "fused" (1, default: one launch per call that runs the
  * per sample-view layers AND the per sample layers, the view-combined activations staying in an L2-resident slab; 0: separate
  * PRE / POST launches with an HBM scratch between them), "post_tiles" (1..8: 64-sample tiles per round of the fused launch),
- * "tail_kb" (0..4: K blocks of every GEMM step issued
+ * "ray_image_width" (W > 0 declares that the rays of every scene passed to the render calls form a row-major image of that width,
+ * e.g. the reference's gen_rays output: the MLP launch then walks them in 16 x 16 pixel tiles, which keeps the gathered feature
+ * map lines in L2; results do not change; 0 = off; diner_render_image sets it by itself), "tail_kb" (0..4: K blocks of every GEMM step issued
  * N-tile-outer so that the first epilogue half overlaps the step's tail), "early_split" (worker/helper split of the next tile's
  * early gather), "sub_batch" (samples per PRE/POST launch pair), "rebuild_maps" (forces the next query to rebuild the hoisted
  * lin_z maps) or "latent_layout" (see diner_set_scene). */

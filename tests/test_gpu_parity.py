@@ -545,6 +545,27 @@ def test_training_steps_reduce_the_loss():
     assert losses[-1] < losses[0]
 
 
+def test_tile_order_of_rays_does_not_change_the_image():
+    """diner_set_option("ray_image_width"): the fused launch walks a row-major image in 16 x 16 pixel tiles (L2 locality of the
+    gathered feature-map lines).  Only the order of the work may change: bit-identical output, also for several scenes per call
+    and for K that is neither a multiple nor a divisor of the 64-sample round."""
+    from diner_b200 import synthetic as S
+    for SB, Hh, Ww, K in ((1, 32, 48, 64), (2, 16, 32, 24), (1, 32, 32, 160)):
+        batch = S.make_scene(Hh, Ww, 4, SB, 1.0, 2.5, 61)
+        latent = torch.randn(SB, 4, 512, (Hh + 128) // 2, (Ww + 128) // 2, generator=torch.Generator().manual_seed(61)) * 0.5
+        model = product_model(batch, latent, S.make_mlp_state(seed=61), "cuda", "parity")
+        rays = S.gen_rays(batch["target_extrinsics"], batch["target_intrinsics"], Ww, Hh, torch.full((SB,), 1.0),
+                          torch.full((SB,), 2.5)).view(SB, Hh * Ww, 8).contiguous().cuda()
+        ctx = model.context()
+        a = ctx.render(rays, K, 100, 8, True, 1, dict(seed=3), want_weights=True)
+        ctx.set_option("ray_image_width", Ww)
+        b = ctx.render(rays, K, 100, 8, True, 1, dict(seed=3), want_weights=True)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), (SB, Hh, Ww, K)
+        ctx.set_option("ray_image_width", Ww - 16)                     # does not divide the ray count: silently the caller's order
+        c = ctx.render(rays, K, 100, 8, True, 1, dict(seed=3))
+        assert torch.equal(a[0], c[0])
+
+
 def test_render_host_entry_matches_device_entry():
     """diner_render_host (plain host buffers in and out, copies and the stream sync inside the call -- the entry a non-torch
     caller binds) must return exactly what diner_render returns for the same rays and seed."""

@@ -17,6 +17,8 @@ rend = NeRFRendererDGS(n_samples=bench.K, n_depth_candidates=bench.C, n_gaussian
 start = (bench.H // 2) * bench.W - n_rays // 2        # rows around the image centre (foreground)
 r = rays[:, start:start + n_rays].contiguous().cuda()
 ctx = model.context()
+if os.environ.get("DINER_RAY_IMAGE_WIDTH") is None:
+    ctx.set_option("ray_image_width", bench.W)        # the slab is whole rows of the row-major image
 ctx.set_timing(True)
 for i in range(reps):
     with torch.no_grad():
