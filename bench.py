@@ -435,7 +435,11 @@ def main():
                          "frac": achieved / pk["sustained"], "peak_source": pk["src"] + " bf16 dense sustained (fp16 runs at the same rate)",
                          "achieved_executed_mma": executed,
                          "executed_note": "tensor-pipe FLOP/s the kernel really issues (lin_z hoisted out, x3 passes in parity mode); burst peak %.1f" % pk["burst"],
-                         "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the newest ncu --set full capture.  The capture
+                         # launches the kernel on a 524 288-sample slab of this workload (ncu replays every launch ~40 times); this run's
+                         # launch covers n_samp_rank samples, so the captured bytes are scaled by the sample ratio
+                         "traffic": tr["dram_bytes_per_launch"] * n_samp_rank / n_pre_launches / 524288.0 if tr else None,
+                         "traffic_captured": {"bytes": tr["dram_bytes_per_launch"], "samples": 524288} if tr else None,
                          "traffic_source": ("ncu --set full, %s" % tr["file"]) if tr else None,
                          "whole_step_frac": rays_per_s / world * K * FLOP_PER_SAMPLE / 1e12 / pk["sustained"],
                          "stage_ms_per_step": stage,
