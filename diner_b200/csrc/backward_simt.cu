@@ -338,10 +338,11 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         BK(tc3_make_map(map_zp, ZP, (size_t)(4 * nkb_max) * 2 * tc::WTILE_BYTES));
     }
     // Y (rows x 512) (+)= act(X (rows x 512)) . W^T + bias   [forward weights packed in tcs->wpack]
-    auto tc_fwd = [&](const float* X, bool relu_in, long long pair0, const float* bias, float* Y, bool accum, long long rows) -> cudaError_t {
+    // (`add` != nullptr: Y = add + ...; lets the residual recurrence write each block input into its own buffer without a copy)
+    auto tc_fwd = [&](const float* X, bool relu_in, long long pair0, const float* bias, float* Y, const float* add, long long rows) -> cudaError_t {
         tc3::Args a{};
         a.bmap = tcs->wmap; a.A = X; a.lda = 512; a.rows = rows; a.K = 512; a.nkb_total = 8; a.relu_a = relu_in; a.b_pair0 = pair0;
-        a.n_slices = 1; a.kb_per_slice = 8; a.C = Y; a.ldc = 512; a.mode = accum ? 1 : 0; a.scale = tc::W_INV; a.bias = bias;
+        a.n_slices = 1; a.kb_per_slice = 8; a.C = Y; a.ldc = 512; a.mode = 0; a.scale = tc::W_INV; a.bias = bias; a.add = add; a.ldd = 512;
         return tc3_gemm(a, grid_pairs, tcs->err_flag, st);
     };
     // GX (rows x 512) (+)= (G (rows x 512) . W) * (mask > 0)   [W^T packed in wt_pack]
@@ -362,8 +363,8 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
     // dW (512 x 512) += G^T . act(X);  db += column sums of G.  `packed` = tc_pack_act(X) (AP or ZP)
     auto tc_wgrad = [&](const float* G, const Tc3Map& pmap, long long rows, float* dW, float* db) -> cudaError_t {
         const long long nkb = (rows + 63) / 64;
-        dim3 tg(512 / 32, (unsigned)(nkb * 2)), tb(32, 8);
-        tc3::transpose_pad_kernel<<<tg, tb, 0, st>>>(G, GT, rows, 512, nkb * 64);   // (rows, 512) -> (512, nkb * 64), zero padded
+        dim3 tg(512 / 32, (unsigned)((nkb * 64 + 255) / 256)), tb(32, 8);
+        tc3::transpose_pad_kernel<<<tg, tb, 0, st>>>(G, GT, rows, 512, nkb * 64, db);   // (rows, 512) -> (512, nkb * 64), zero padded; db += column sums
         g_launches++;
         tc3::Args a{};
         a.bmap = pmap.map; a.A = GT; a.lda = nkb * 64; a.rows = 512; a.K = rows; a.nkb_total = (int)nkb; a.relu_a = 0; a.b_pair0 = 0;
@@ -374,12 +375,6 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         a.n_slices = (int)((nkb + a.kb_per_slice - 1) / a.kb_per_slice);
         a.C = dW; a.ldc = 512; a.mode = 2; a.scale = 1.0f;
         BK(tc3_gemm(a, grid_pairs, tcs->err_flag, st));
-        if (db) {
-            const long long per = 256;                                                  // 2 x rows/256 CTAs: enough loads in flight for HBM
-            dim3 cg(2, (unsigned)((rows + per - 1) / per));
-            tc3::colsum_kernel<<<cg, 256, 0, st>>>(G, 512, rows, 512, per, db);
-            g_launches++;
-        }
         return cudaGetLastError();
     };
 
@@ -394,10 +389,9 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         BK((linear<false, false>(xin, ld_in, m.w_in, m.d_in, m.b_in, x, Hd, R, m.d_in, Hd, st)));
         for (int b = 0; b < n_pre; ++b) {
             if (use_tc) {
-                BK(tc_fwd(zlat, false, pair_z[b], m.b_z[b], x, true, R));
-                BK(cudaMemcpyAsync(xa[b], x, (size_t)R * Hd * sizeof(float), cudaMemcpyDeviceToDevice, st));
-                BK(tc_fwd(x, true, pair_0[b], m.b_fc0[b], net[b], false, R));
-                BK(tc_fwd(net[b], true, pair_1[b], m.b_fc1[b], x, true, R));
+                BK(tc_fwd(zlat, false, pair_z[b], m.b_z[b], xa[b], x, R));               // xa[b] = x + lin_z[b](z)
+                BK(tc_fwd(xa[b], true, pair_0[b], m.b_fc0[b], net[b], nullptr, R));
+                BK(tc_fwd(net[b], true, pair_1[b], m.b_fc1[b], x, xa[b], R));              // x = xa[b] + fc_1(relu(net))
                 continue;
             }
             BK((linear<false, true>(zlat, L, m.w_z[b], L, m.b_z[b], x, Hd, R, L, Hd, st)));
@@ -412,8 +406,8 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
             const int B = n_pre + b;
             BK(cudaMemcpyAsync(xci[b], xc, (size_t)ns * Hd * sizeof(float), cudaMemcpyDeviceToDevice, st));
             if (use_tc) {
-                BK(tc_fwd(xc, true, pair_0[B], m.b_fc0[B], netc[b], false, ns));
-                BK(tc_fwd(netc[b], true, pair_1[B], m.b_fc1[B], xc, true, ns));
+                BK(tc_fwd(xci[b], true, pair_0[B], m.b_fc0[B], netc[b], nullptr, ns));
+                BK(tc_fwd(netc[b], true, pair_1[B], m.b_fc1[B], xc, xci[b], ns));
                 continue;
             }
             BK((linear<true, false>(xc, Hd, m.w_fc0[B], Hd, m.b_fc0[B], netc[b], Hd, ns, Hd, Hd, st)));
@@ -449,7 +443,7 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         }
         combine_backward_kernel<<<grid1d(R * Hd), 256, 0, st>>>(gxc, gx, ns, s.NV, Hd);
         g_launches++;
-        BK(cudaMemsetAsync(gz, 0, (size_t)R * L * sizeof(float), st));
+        if (!use_tc) BK(cudaMemsetAsync(gz, 0, (size_t)R * L * sizeof(float), st));     // (the tcgen05 path stores the first block's contribution)
         for (int b = n_pre - 1; b >= 0; --b) {
             // x_out = xa + fc_1(relu(net)),  net = fc_0(relu(xa)),  xa = x_prev + lin_z[b](zlat);  gx = dL/dx_out
             if (use_tc) {
@@ -461,7 +455,7 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
                 BK(tc_wgrad(gnet, map_ap, R, g_w0[b], g_b0[b]));
                 BK(tc_dgrad(gnet, 2 * b, xa[b], gx, true, R));                               // gx += (gnet W0) * (xa > 0)  = dL/dxa
                 BK(tc_wgrad(gx, map_zp, R, g_wz[b], g_bz[b]));
-                BK(tc_dgrad(gx, 2 * m.n_blocks + b, nullptr, gz, true, R));                  // gz += gx W_z
+                BK(tc_dgrad(gx, 2 * m.n_blocks + b, nullptr, gz, b != n_pre - 1, R));        // gz (+)= gx W_z
                 continue;
             }
             BK((wgrad<true>(gx, Hd, net[b], Hd, R, Hd, Hd, g_w1[b], g_b1[b], st)));

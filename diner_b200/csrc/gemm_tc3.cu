@@ -359,21 +359,41 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
     }
 }
 
-// (rows, cols) -> (cols, ld_dst) with ld_dst >= rows (a multiple of 64 so that the GEMM's 16-byte loads stay aligned)
-__global__ void transpose_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int cols, long long ld_dst) {
+// (rows, cols) -> (cols, ld_dst) with ld_dst >= rows (a multiple of 64 so that the GEMM's 16-byte loads stay aligned), zero padded;
+// optionally colsum[c] += sum_r src[r][c] on the way (the bias gradient: G is read once for both).  One CTA = 32 columns x 256 rows.
+__global__ void transpose_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int cols, long long ld_dst,
+                                     float* __restrict__ colsum) {
     __shared__ float tile[32][33];
-    const long long r0 = (long long)blockIdx.y * 32;
+    __shared__ float part[8][32];
     const int c0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const long long r = r0 + i;
-        const int c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[r * cols + c] : 0.0f;
+    float s = 0.0f;                                      // thread (x, y): column c0 + x, rows y, y + 8, ...
+    for (int sub = 0; sub < 8; ++sub) {
+        const long long r0 = ((long long)blockIdx.y * 8 + sub) * 32;
+        if (r0 >= ld_dst) break;
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const long long r = r0 + i;
+            const int c = c0 + threadIdx.x;
+            const float v = (r < rows && c < cols) ? src[r * cols + c] : 0.0f;
+            tile[i][threadIdx.x] = v;
+            s += v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const int c = c0 + i;
+            const long long r = r0 + threadIdx.x;
+            if (c < cols && r < ld_dst) dst[(long long)c * ld_dst + r] = tile[threadIdx.x][i];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i;
-        const long long r = r0 + threadIdx.x;
-        if (c < cols && r < ld_dst) dst[(long long)c * ld_dst + r] = tile[threadIdx.x][i];
+    if (colsum) {
+        part[threadIdx.y][threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.y == 0 && c0 + threadIdx.x < cols) {
+            float t = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
+            atomicAdd(colsum + c0 + threadIdx.x, t);
+        }
     }
 }
 
