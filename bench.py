@@ -235,6 +235,35 @@ def train_bench(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    # gradient check (outside the timed region): diner_render_backward against the loss / gradient digests of the UNMODIFIED
+    # reference's autograd (tests/golden/grads_cfg1_face64.pt, produced by oracle/make_golden.py)
+    grad_check = None
+    try:
+        from oracle import diner_oracle as O
+        from oracle import make_golden as MG
+        from diner_b200.nerf_renderer import mlp_param_order
+        gg = torch.load(os.path.join(ROOT, "tests", "golden", "grads_cfg1_face64.pt"))
+        cfg_g, batch_g, latent_g, mlp_g, rays_g, _, gt_g = MG.grad_case_inputs()
+        mg = product_model(batch_g, latent_g, mlp_g, dev, args.mode)
+        cg = mg.context()
+        rg, zg = rays_g.to(dev), gg["z"].to(dev).contiguous()
+        _, rgb_g, _ = cg.composite(rg, zg, cfg_g["white"], mg.mode_id(), want_weights=False)
+        g_rgb = (2.0 * (rgb_g - gt_g.to(dev)) / rgb_g.numel()).contiguous()
+        gp, dl = cg.render_backward(rg, zg, cfg_g["white"], g_rgb, None, True, tuple(latent_g.shape))
+        worst, off = 0.0, 0
+        named = dict(mg.mlp_fine.named_parameters())
+        for k in mlp_param_order(mg.mlp_fine):
+            n = named[k].numel()
+            d = O.grad_digest(gp[off:off + n].cpu(), 256)
+            worst = max(worst, abs(d["norm"] - gg["grads"][k]["norm"]) / max(gg["grads"][k]["norm"], 1e-30))
+            off += n
+        dlat = O.grad_digest(dl.cpu(), 4096)
+        grad_check = {"reference": "unmodified reference autograd (tests/golden/grads_cfg1_face64.pt)",
+                      "loss_abs_err": abs(float(((rgb_g.cpu() - gt_g) ** 2).mean()) - gg["loss"]),
+                      "worst_param_grad_norm_rel_err": worst,
+                      "latent_grad_norm_rel_err": abs(dlat["norm"] - gg["latent_grad"]["norm"]) / gg["latent_grad"]["norm"]}
+    except Exception as e:                       # reported extra, never allowed to break the line
+        grad_check = {"unavailable": repr(e)[:200]}
     rays_step = SBt * RB
     flop = 3 * rays_step * Kt * (4774912 * NVt + 2101248)          # forward + ~2x for dgrad + wgrad
     print(json.dumps({"metric": "train_rays_per_sec", "value": rays_step / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1,
@@ -244,7 +273,7 @@ def train_bench(args):
                       "data": "synthetic",
                       "config": {"workload": "Facescape-shaped synthetic training step: SB=4 x 256x256, 4 src views, 128 samples/ray, "
                                              "4096 rays/scene, MSE + backward + Adam", "mode": args.mode},
-                      "loss": float(loss), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12}))
+                      "loss": float(loss), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "grad_check": grad_check}))
 
 
 def latest_traffic():
