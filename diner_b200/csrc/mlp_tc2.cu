@@ -821,15 +821,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     ++ph0; ++ph1;
                 }
             }
-            // last fc_1: a worker warp combines only its own N tile of x, so the n2 == 0 warps start on bar_acc0.  They skip
-            // this phase of bar_acc, which is safe: their next wait on it follows a wait on the NEXT phase of bar_acc0, and the
-            // commits of one issuer complete in order
-            const uint32_t it_last = it;
-            if (!helper) {
-                mbar_wait(bar_acc0, it & 1, a.err, 43);
-                if (n2 == 1) mbar_wait(bar_acc, it & 1, a.err, 38);
-                ++it;
-            }
+            // last fc_1: the view combine reads x.  Every worker warp takes two 32-column chunks of N tile 0 as soon as that tile is
+            // complete (bar_acc0, under the n1 tail of the GEMM) and two chunks of N tile 1 after the whole step: both warps of a TMEM
+            // lane quarter can read any column, so the part of the combine that follows the GEMM is half of what it would be if
+            // each warp kept to its own N tile
+            if (!helper) mbar_wait(bar_acc0, it & 1, a.err, 43);
             TSW();
             tc_fence_after();
             // combine: mean over the NV adjacent rows (lanes) of each sample, sequential like torch.mean (resnetfc.py:148-151)
@@ -839,10 +835,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             const bool wr = FUSED || (live && smp < a.n_samples);
             float* dst_sample = a.xc + (size_t)(FUSED ? xc_row0 + r / a.NV : (wr ? smp : 0)) * HID;
 #pragma unroll 1
-            for (int c32 = 0; c32 < ((helper || (a.dbg_skip & 128)) ? 0 : 4); ++c32) {
+            for (int ci = 0; ci < ((helper || (a.dbg_skip & 128)) ? 0 : 4); ++ci) {
+                const int nt = ci >> 1, c32 = 2 * n2 + (ci & 1);                 // N tile of the chunk, chunk within the tile
+                if (ci == 2) {
+                    mbar_wait(bar_acc, it & 1, a.err, 38);                        // N tile 1 = the whole step
+                    tc_fence_after();
+                }
                 uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
-                const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * nt + 32 * c32), v);
+                const int h0 = 256 * nt + 128 * (q >> 1) + 32 * c32;
                 switch (a.NV) {
                     case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
                     case 2: combine_store<2>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
@@ -852,6 +853,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     default: combine_store<32>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
                 }
             }
+            if (!helper) ++it;
             tc_fence_before();
             TSW();
             if (has_next && !helper) {
@@ -861,9 +863,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 TSW();
             }
             if (FUSED && !has_next && !helper) {
-                // the POST tile overwrites TMEM X and the whole A operand: the last fc_1 must be complete (the n2 == 0 warps only
-                // waited for its N tile 0 above), every worker done reading X, and the x_c slab rows visible to the whole CTA
-                if (n2 == 0) mbar_wait(bar_acc, it_last & 1, a.err, 37);
+                // the POST tile overwrites TMEM X and the whole A operand: the last fc_1 is complete (every worker waited for it in
+                // the combine), every worker must be done reading X, and the x_c slab rows visible to the whole CTA
                 __threadfence_block();
                 asm volatile("bar.sync 10, %0;" ::"n"(NUM_WORKERS) : "memory");
             }
