@@ -119,8 +119,10 @@ def strided_pick(n_rays):
     return (torch.arange(n_rays) * (H * W // n_rays) + 131) % (H * W)
 
 
-def cpu_baseline(batch, latent, mlp, rays, n_rays=12288, warm=256):
-    """The oracle port (torch-CPU restatement pinned to the reference) on this box's host cores, bounded sample."""
+def cpu_baseline(batch, latent, mlp, rays, n_rays=12288, warm=256, check=None):
+    """The oracle port (torch-CPU restatement pinned to the reference) on this box's host cores, bounded sample.
+    `check(rays_sample, noise, rgb, depth, z)` (optional) is handed the sample and the oracle's outputs for it: this leg is the
+    one place of the bench where the oracle runs, so the parity numbers of the line are taken from the same run."""
     from oracle import diner_oracle as O
     from diner_b200 import synthetic as S
     scene = O.make_scene_state(batch, latent, mlp)
@@ -129,15 +131,18 @@ def cpu_baseline(batch, latent, mlp, rays, n_rays=12288, warm=256):
 
     def run(rr):
         n = rr.shape[1]
-        return O.render(scene, rr, K, C, G, WHITE, S.hash_uniform((1, n, C), 1, 1), S.hash_normal((1, n, G), 1, 2),
-                        S.hash_uniform((1, n, K), 1, 3))
+        noise = dict(u_coarse=S.hash_uniform((1, n, C), 1, 1), g_noise=S.hash_normal((1, n, G), 1, 2), u_fill=S.hash_uniform((1, n, K), 1, 3))
+        return noise, O.render(scene, rr, K, C, G, WHITE, noise["u_coarse"], noise["g_noise"], noise["u_fill"], return_z=True)
     with torch.no_grad():
         run(r[:, :warm])
         t0 = time.time()
-        run(r)
+        noise, (rgb_o, dep_o, _, z_o) = run(r)
         dt = time.time() - t0
-    return dict(value=n_rays / dt, unit="rays/s", cores=torch.get_num_threads(), kind="port",
-                sample="%d rays of the 512x512 workload (strided), oracle/diner_oracle.py on torch-CPU fp32, %.1f s" % (n_rays, dt))
+    out = dict(value=n_rays / dt, unit="rays/s", cores=torch.get_num_threads(), kind="port",
+               sample="%d rays of the 512x512 workload (strided), oracle/diner_oracle.py on torch-CPU fp32, %.1f s" % (n_rays, dt))
+    if check is not None:
+        out["_parity"] = check(r, noise, rgb_o, dep_o, z_o)
+    return out
 
 
 def gpu_eager_baseline(batch, latent, mlp, rays, dev, n_rays=4096):
@@ -290,29 +295,24 @@ def latest_traffic():
     return best
 
 
-def parity_check(model, rend_cfg, batch, latent, mlp, rays, dev, n_rays=2048):
-    """Rendered output of the CUDA path vs the oracle (torch-CPU port pinned to the reference) on a bounded strided sample of
-    the workload's rays, outside every timed region: stage-wise on the oracle's own sample depths (max |err| over all rays,
-    the 1e-4 bar) and end to end with the same injected noise (PSNR; rays beyond 1e-4 come from erf-ulp shortlist flips
-    between torch-CPU and CUDA, tests/test_gpu_parity.py)."""
-    from oracle import diner_oracle as O
-    from diner_b200 import synthetic as S
-    scene = O.make_scene_state(batch, latent, mlp)
-    r = rays[:, strided_pick(n_rays)].contiguous()
-    noise = dict(u_coarse=S.hash_uniform((1, n_rays, C), 1, 1), g_noise=S.hash_normal((1, n_rays, G), 1, 2),
-                 u_fill=S.hash_uniform((1, n_rays, K), 1, 3))
-    with torch.no_grad():
-        rgb_o, dep_o, _, z_o = O.render(scene, r, K, C, G, WHITE, noise["u_coarse"], noise["g_noise"], noise["u_fill"], return_z=True)
-        ctx = model.context()
-        _, rgb_s, dep_s = ctx.composite(r.to(dev), z_o.to(dev).contiguous(), WHITE, model.mode_id(), want_weights=False)
-        rgb_e, dep_e, _, _ = ctx.render(r.to(dev), K, C, G, WHITE, model.mode_id(), {k: v.to(dev).contiguous() for k, v in noise.items()})
-    e_rgb, e_dep = float((rgb_s.cpu() - rgb_o).abs().max()), float((dep_s.cpu() - dep_o).abs().max())
-    e2e = torch.maximum((rgb_e.cpu() - rgb_o).abs().max(-1).values, (dep_e.cpu() - dep_o).abs())
-    return {"rays": n_rays, "reference": "oracle/diner_oracle.py on torch-CPU (pinned to the reference's goldens)",
-            "max_abs_err_rgb": e_rgb, "max_abs_err_depth": e_dep, "psnr_vs_ref_db": O.psnr(rgb_s.cpu(), rgb_o),
-            "stage": "given the oracle's sample depths (every ray)",
-            "end_to_end": {"psnr_vs_ref_db": O.psnr(rgb_e.cpu(), rgb_o), "median_abs_err": float(e2e.median()),
-                           "frac_rays_beyond_1e-4": float((~(e2e <= 1e-4)).float().mean())}}
+def parity_block(model, dev):
+    """-> check callback for cpu_baseline: the CUDA path on the SAME rays and noise as the oracle run of the cpu_baseline leg,
+    outside every timed region.  Stage-wise on the oracle's own sample depths (max |err| over all rays: the 1e-4 bar) and end to end
+    with the same injected noise (PSNR; the rays beyond 1e-4 there are erf-ulp shortlist flips between torch-CPU and CUDA, which
+    tests/test_gpu_parity.py resolves against the oracle run on cuda)."""
+    def check(r, noise, rgb_o, dep_o, z_o):
+        from oracle.diner_oracle import psnr
+        with torch.no_grad():
+            ctx = model.context()
+            _, rgb_s, dep_s = ctx.composite(r.to(dev), z_o.to(dev).contiguous(), WHITE, model.mode_id(), want_weights=False)
+            rgb_e, dep_e, _, _ = ctx.render(r.to(dev), K, C, G, WHITE, model.mode_id(), {k: v.to(dev).contiguous() for k, v in noise.items()})
+        e2e = torch.maximum((rgb_e.cpu() - rgb_o).abs().max(-1).values, (dep_e.cpu() - dep_o).abs())
+        return {"rays": int(r.shape[1]), "reference": "oracle/diner_oracle.py on torch-CPU (pinned to the reference's goldens), the cpu_baseline run",
+                "max_abs_err_rgb": float((rgb_s.cpu() - rgb_o).abs().max()), "max_abs_err_depth": float((dep_s.cpu() - dep_o).abs().max()),
+                "psnr_vs_ref_db": psnr(rgb_s.cpu(), rgb_o), "stage": "given the oracle's sample depths (every ray)",
+                "end_to_end": {"psnr_vs_ref_db": psnr(rgb_e.cpu(), rgb_o), "median_abs_err": float(e2e.median()),
+                               "frac_rays_beyond_1e-4": float((~(e2e <= 1e-4)).float().mean())}}
+    return check
 
 
 def main():
@@ -361,8 +361,11 @@ def main():
     def packed_render(r, out, ray_offset):
         rend.render_packed(model, r, out=out, ray_offset=ray_offset)    # compositing kernel writes rgb|depth into the gather slice
 
+    weights = None
+
     def step(src):
-        return render_sharded(packed_render, src, packed=True, return_packed=True)   # one in-place NCCL all-gather per image when world > 1
+        # one in-place NCCL all-gather per image when world > 1; shards are whole image rows, weighted by the measured speed of each GPU
+        return render_sharded(packed_render, src, packed=True, return_packed=True, weights=weights, align=W)
 
     def sync():
         if world > 1:
@@ -372,6 +375,21 @@ def main():
     for _ in range(args.warmup):
         step(rays_dev)
     sync()
+    if world > 1 and os.environ.get("DINER_BALANCE", "1") != "0":
+        # the GPUs of a box do not run at the same clock under the power cap: time this rank's equal shard once more (device time of
+        # its own kernels only), gather the times and re-cut the shards proportionally (multi_gpu.balance_weights); two untimed steps
+        from diner_b200.multi_gpu import balance_weights
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tmp = torch.empty(1, hi - lo, 4, device=dev)
+        a0.record()
+        packed_render(rays_dev[:, lo:hi], tmp, lo)
+        a1.record()
+        torch.cuda.synchronize()
+        weights = balance_weights(a0.elapsed_time(a1) * 1e-3)
+        from diner_b200.multi_gpu import shard_bounds
+        lo, hi, _ = shard_bounds(n_total, world, rank, weights, W)       # this rank's shard from here on (roofline bookkeeping below)
+        step(rays_dev)
+        sync()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -450,7 +468,7 @@ def main():
             "run": {"mode": args.mode, "rays_per_step": n_total, "sharding": "rays/%d" % world,
                     "l2": "inputs larger than L2 (%.1f GB fp32 lin_z maps gathered per sample-view, %.0f MB of sample depths + per-sample outputs per step)"
                           % (3 * NV * ((H + 128) // 2) * ((W + 128) // 2) * 512 * 4 / 1e9, n_total * K * 20 / 1e6),
-                    "tail_kb": int(os.environ.get("DINER_TC_TAIL_KB", "-1")),
+                    "shard_weights": [round(x / max(weights), 4) for x in weights] if weights else None,
                     "e2e_path": "diner_render_host (C ABI, host buffers)" if world == 1 else "pinned host rays -> sharded render + all-gather -> host image"},
             "e2e": {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                     "h2d_bytes_per_step": rays_host.numel() * 4, "d2h_bytes_per_step": e2e_d2h},
@@ -474,10 +492,9 @@ def main():
                          "stage_ms_per_step": stage,
                          "once_per_scene_ms": {"lin_z_maps (hoisted lin_z over all latent pixels, excluded from the step like the scene encode)": scene_prepare_ms}},
         }
-        if world == 1 and args.workload == "dtu512" and not args.rays:
-            line["parity"] = parity_check(model, None, batch, latent, mlp, rays, dev)
         if not args.no_cpu_baseline and world == 1 and args.workload == "dtu512" and not args.rays:
-            line["cpu_baseline"] = cpu_baseline(batch, latent, mlp, rays)
+            line["cpu_baseline"] = cpu_baseline(batch, latent, mlp, rays, check=parity_block(model, dev))
+            line["parity"] = line["cpu_baseline"].pop("_parity")
             try:
                 del model
                 torch.cuda.empty_cache()

@@ -35,6 +35,9 @@ def _worker(rank, world, port, n_rays, q):
         rgb_p, depth_p = render_sharded(packed, rr, packed=True)
         c, d = _fake_render(rr)
         ok = ok and bool(torch.equal(rgb_p, c) and torch.equal(depth_p, d))
+        for w in ([3.0, 1.0], [1.0, 1e6]):                # weighted shards (speed-balanced sharding), incl. an almost empty one
+            rgb_w, depth_w = render_sharded(packed, rr, packed=True, weights=w, align=4 if n_rays % 4 == 0 else 1)
+            ok = ok and bool(torch.equal(rgb_w, c) and torch.equal(depth_w, d))
     q.put((rank, ok, tuple(rgb.shape)))
     dist.destroy_process_group()
 
@@ -60,9 +63,15 @@ def test_sharded_render_matches_single(n_rays):
 def test_shard_bounds_cover_everything():
     for n in (0, 1, 7, 64, 262144):
         for world in (1, 2, 3, 8):
-            spans = [shard_bounds(n, world, r)[:2] for r in range(world)]
-            assert spans[0][0] == 0 and spans[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            for weights, align in ((None, 1), ([1.0 + 0.05 * r for r in range(world)], 1), ([1.0 + 0.05 * r for r in range(world)], 512)):
+                spans = [shard_bounds(n, world, r, weights, align) for r in range(world)]
+                assert spans[0][0] == 0 and spans[-1][1] == n
+                assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+                assert all(hi - lo <= per for lo, hi, per in spans) and len({per for _, _, per in spans}) == 1
+                if weights is not None and align > 1:
+                    assert all(lo % align == 0 for lo, _, _ in spans)
+    lo, hi, _ = shard_bounds(262144, 8, 7, [1.0] * 7 + [1.1], 512)
+    assert hi - lo > 262144 // 8                             # the faster rank gets more rays
 
 
 def test_bench_sample_indices_in_range():

@@ -25,7 +25,9 @@ rays = S.gen_rays(batch["target_extrinsics"], batch["target_intrinsics"], W, H, 
 rays = rays[:, :H * W - 5].contiguous().to(dev)            # ragged: not a multiple of the world size
 whole = rend.render_packed(model, rays)
 img = render_sharded(lambda r, out, off: rend.render_packed(model, r, out=out, ray_offset=off), rays, packed=True, return_packed=True)
-ok = torch.tensor([int(torch.equal(img, whole))], device=dev)
+img_w = render_sharded(lambda r, out, off: rend.render_packed(model, r, out=out, ray_offset=off), rays, packed=True, return_packed=True,
+                       weights=[1.0 + 0.07 * ((r * 5) % world) for r in range(world)])          # speed-weighted (uneven) shards
+ok = torch.tensor([int(torch.equal(img, whole) and torch.equal(img_w, whole))], device=dev)
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("sharded render over %d GPUs == single-GPU render, bit for bit, on every rank: %s  (%d rays, rgb mean %.4f)" % (
