@@ -375,9 +375,10 @@ def main():
     for _ in range(args.warmup):
         step(rays_dev)
     sync()
-    if world > 1 and os.environ.get("DINER_BALANCE", "1") != "0":
-        # the GPUs of a box do not run at the same clock under the power cap: time this rank's equal shard once more (device time of
-        # its own kernels only), gather the times and re-cut the shards proportionally (multi_gpu.balance_weights); two untimed steps
+    if world > 1 and os.environ.get("DINER_BALANCE", "0") == "1":
+        # optional (off by default: measured on 8 B200s the per-GPU time differences of one step are noise, not persistent speed
+        # differences -- balanced shards 91.6 ms vs equal shards 89.4 ms per image): time this rank's equal shard once more, gather the
+        # times and re-cut the shards proportionally (multi_gpu.balance_weights)
         from diner_b200.multi_gpu import balance_weights
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tmp = torch.empty(1, hi - lo, 4, device=dev)

@@ -10,11 +10,11 @@ gather buffer (diner_render_rgbd) and the collective runs in place, so between t
 render and ncclAllGather there is no pack / copy pass; for one scene per call (SB = 1, the inference
 case) and equal shards the gathered buffer IS the image and the returned rgb / depth are views of it.
 
-Shards may be weighted (`weights`, one positive number per rank): under the 1 kW power cap the GPUs of
-a box do not run at the same clock, and with equal shards every rank waits at the collective for the
-slowest one (measured: 5 % of the step at 8 GPUs).  `balance_weights` turns per-rank render times into
-weights; shard boundaries stay multiples of `align` rays (whole image rows keep the 2-D tile order of
-the fused launch).
+Shards may be weighted (`weights`, one positive number per rank) for boxes whose GPUs differ in speed;
+`balance_weights` turns per-rank render times into weights and shard boundaries stay multiples of
+`align` rays (whole image rows keep the 2-D tile order of the fused launch).  On the 8 x B200 box of
+this project the per-GPU differences of a step turned out to be run-to-run noise under the power cap,
+not persistent speed differences, so `bench.py` keeps equal shards (DINER_BALANCE=1 enables it).
 """
 import torch
 import torch.distributed as dist
