@@ -207,11 +207,25 @@ def make_gen_rays_golden(ns, outdir):
     torch.save(out, os.path.join(outdir, "gen_rays.pt"))
 
 
+def make_softplus_golden(ns, outdir):
+    """Output of the UNMODIFIED reference ResnetFC with Softplus activations (beta = 2, resnetfc.py:124-127) on hashed inputs:
+    pins the oracle's (and through it the fp32 kernels') Softplus branch."""
+    sd = S.make_mlp_state(d_in=55, d_latent=32, d_hidden=64, seed=2)
+    net = ns.resnetfc.ResnetFC(55, 4, 5, 32, 64, beta=2.0, combine_layer=3)
+    net.load_state_dict(sd)
+    zx = S.hash_normal((2, 4, 9, 32 + 55), 3)
+    with torch.no_grad():
+        out = net(zx, combine_dim=1)
+    torch.save(dict(beta=2.0, mlp_args=dict(d_in=55, d_latent=32, d_hidden=64, seed=2), zx_args=((2, 4, 9, 87), 3), out=out.contiguous()),
+               os.path.join(outdir, "softplus_resnetfc.pt"))
+
+
 def main():
     ns = ref_import.load()
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
     make_gen_rays_golden(ns, outdir)
+    make_softplus_golden(ns, outdir)
     if "--rays-only" in sys.argv:
         return
     if "--extra-only" not in sys.argv:
