@@ -147,7 +147,7 @@ extern "C" int diner_set_mlp(diner_ctx* c, int d_in, int d_latent, int d_hidden,
     }
     c->mlp = m;
     c->has_mlp = true;
-    // tensor-core packing (bf16 hi/lo tiles in UMMA layout); shapes it cannot serve leave tc.ready = false
+    // tensor-core packing (fp16 hi/lo tiles of 64 w in UMMA layout); shapes it cannot serve leave tc.ready = false
     cudaError_t e = tc_pack_weights(c->tc, m, st);
     if (e != cudaSuccess) return fail(DINER_E_CUDA, "tc_pack_weights: %s", cudaGetErrorString(e));
     return DINER_OK;

@@ -1,8 +1,13 @@
-// tcgen05 path, second generation: CTA-PAIR kernel (cta_group::2).
+// tcgen05 path of the per-sample network (PixelNeRF.forward + ResnetFC.forward): the CTA-PAIR kernel (cta_group::2).
 //
-// Why (profiles/r1_ncu_mlp_pre_parity.md, tools/mma_probe.cu): in the single-CTA kernel (mlp_tc.cu) every MMA is
-// 128x64x16 and reads 6 KiB of shared memory for 32 cycles of math, and every SM streams the complete weight set per
-// 64 rows -- shared-memory bandwidth, not the tensor pipe, bounds it.  Here two CTAs of a cluster form one UMMA:
+// Kinds of one kernel template: FUSED (default: per 64 samples, NV tiles of 64 sample-view rows -- lin_in, per block the Y_b
+// gather, fc_0, fc_1, view mean -- then one tile of 64 samples -- remaining blocks, lin_out -- with the view-combined
+// activations in an L2-resident per-CTA slab), PRE / POST (the same two halves as separate launches with an HBM scratch,
+// bit-identical: A/B reference), ZMAP (the once-per-scene Y maps).
+//
+// Why a CTA pair (tools/mma_probe.cu, round 1): in a single-CTA kernel with 64 rows per CTA every MMA is 128x64x16 and reads
+// 6 KiB of shared memory for 32 cycles of math, and every SM streams the complete weight set per 64 rows -- shared-memory
+// bandwidth, not the tensor pipe, bounds it.  Here two CTAs of a cluster form one UMMA:
 //   D[128 rows x 256 hidden] += A[128 rows x 16] . B[256 hidden x 16]^T          (tcgen05.mma.cta_group::2, M=128, N=256)
 //   A = activations, K-major: each CTA holds its own 64 rows          (2 KiB per MMA per SM)
 //   B = weights, K-major (the reference's (out,in) layout): each CTA holds 128 of the 256 hidden rows (4 KiB per MMA per SM)
@@ -18,7 +23,7 @@
 // lin_z is hoisted out of the per-sample work: grid_sample(bilinear) and lin_z are both linear, so
 //   lin_z[b](bilinear(latent, uv)) == bilinear(lin_z[b](latent), uv)      (the four tap weights sum to 1)
 // and Y_b = W_z[b] . latent is computed ONCE per (scene, weights) for every latent pixel by the ZMAP variant of this kernel
-// (bf16x3, fp32 maps [b][pixel][512]).  The PRE kernel then gathers Y_b bilinearly and adds it to the fp32 residual in TMEM:
+// (fp16x3, fp32 maps [b][pixel][512]).  The PRE kernel then gathers Y_b bilinearly and adds it to the fp32 residual in TMEM:
 // one third of the per-sample-view GEMM work and weight streaming disappears.  The biases that enter a block (b_in / b_fc1[b-1],
 // b_z[b]) are folded into Y_b; b_fc0 is added by the net epilogue, b_fc1 of the last block when the combined x_c is written.
 //
@@ -76,7 +81,7 @@ constexpr int WTILE_BYTES = 128 * KBLK * 2; // 16 KiB: 128 hidden rows x 64 k, K
 constexpr int SMALL_TILE_BYTES = 16 * KBLK * 2; // 2 KiB: the first 16 rows of a weight tile (lin_out)
 constexpr int TILE_SMALL = 1 << 30;             // tile-table flag: load only SMALL_TILE_BYTES of this tile
 constexpr int ACT_KB_BYTES = ROWS * 128;    // 8 KiB per 64-wide K block of the activation operand
-constexpr int ACT_BYTES = ACT_KB_BYTES * (HID / KBLK);   // 64 KiB per bf16 copy
+constexpr int ACT_BYTES = ACT_KB_BYTES * (HID / KBLK);   // 64 KiB per fp16 copy
 constexpr int NUM_THREADS = 512;
 constexpr int NUM_PRODUCERS = 3;               // warps 0,2,3: each CTA streams only half of every weight tile (~33 B/clk needed)
 constexpr int WORKER_WARP0 = 4;
@@ -208,7 +213,7 @@ template <bool PARITY> struct Cfg {
 };
 
 // ---- worker building blocks ----------------------------------------------------------------------
-// TMEM region (this warp's N tile: 128 columns) + per-column bias -> relu -> bf16 hi/lo chunks of the A operand
+// TMEM region (this warp's N tile: 128 columns) + per-column bias -> relu -> fp16 hi/lo chunks of the A operand
 // 32 accumulator columns of row r (hidden h0..h0+31): relu(acc * W_INV + bias) -> four 16-byte K-major chunks (hi / lo)
 template <bool PARITY>
 __device__ __forceinline__ void convert32(const uint32_t* v, const float* __restrict__ bias, int h0, int r, uint8_t* Ahi, uint8_t* Alo) {
@@ -425,7 +430,7 @@ __device__ __forceinline__ void epilogue_add_y_half(uint32_t tmem, uint8_t* Ahi,
     tmem_st_wait();
 }
 
-// ZMAP: 64 latent pixels (rows) x L channels -> bf16 hi/lo A operand; consecutive threads take consecutive 8-channel chunks
+// ZMAP: 64 latent pixels (rows) x L channels -> fp16 hi/lo A operand; consecutive threads take consecutive 8-channel chunks
 __device__ __forceinline__ void load_latent_rows(const Args& a, long long tile, int wt, uint8_t* Ahi, uint8_t* Alo) {
     const int cpr = a.s.L >> 3;                     // 8-channel chunks per row
 #pragma unroll 2
@@ -1012,7 +1017,7 @@ cudaError_t launch(const Args& a, int grid, cudaStream_t st) {
 
 // Per-rank weight tile tables of the pair kernel.  Ring-use order of CTA rank r = for each GEMM step, for kb, for n2:
 // tile (2*n2 + r) of that layer; every entry is a 16 KiB tile index into the packed stream ([hi][lo] per tile pair).
-// Layout of t.table2: [zmap r0][zmap r1][pre r0][pre r1][post r0][post r1]; zmap is always bf16x3.
+// Layout of t.table2: [zmap r0][zmap r1][pre r0][pre r1][post r0][post r1]; zmap is always fp16x3.
 static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cudaStream_t st) {
     using namespace tc2;
     const int kbz = m.d_latent / KBLK, kbh = HID / KBLK;
@@ -1072,7 +1077,7 @@ static cudaError_t tc2_grid_cap(TcState& t, int num_sms, int* cap) {
     return cudaSuccess;
 }
 
-// Y_b = W_z[b] . latent for every latent pixel (bf16x3): once per (scene, weights); see the header comment.
+// Y_b = W_z[b] . latent for every latent pixel (fp16x3): once per (scene, weights); see the header comment.
 static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int grid_cap, cudaStream_t st) {
     using namespace tc2;
     const long long n_pix = (long long)s.SB * s.NV * s.Hl * s.Wl;
