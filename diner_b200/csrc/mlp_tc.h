@@ -31,6 +31,7 @@ struct TcState {
     bool wmap_ok = false;
     CUtensorMap wmap_small;       // same buffer, box = first 16 rows of a tile (2 KiB): lin_out in the pair kernel
     bool wmap_small_ok = false;
+    int early_lin = 0;            // pair kernel PRE tiles: next tile's lin_in issued behind the last fc_1 into the other TMEM half
     int early_split = 0;          // pair kernel PRE: worker/helper split of the next tile's early Y_0 gather (0 = same as inside a tile)
     int dbg_skip = 0;             // profiling experiments (pair kernel PRE): see tc2::Args::dbg_skip
     bool timing = false;          // per-kernel CUDA-event timing (adds one sync per sub-batch)

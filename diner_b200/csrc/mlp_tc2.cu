@@ -144,6 +144,7 @@ struct Args {
                                 // (the Y-map lines gathered by neighbouring rays stay in L2); 0 = process in the caller's order
     int early_worker_kb_hi;     // next-tile Y_0 gather under the last fc_1: K blocks 1..this on the workers, the rest on the helpers
     int worker_kb_hi;           // Y_b gather inside a tile: K blocks 0..this on the workers (released before the N-outer tail), the rest on the helpers
+    int early_lin;              // PRE tiles: issue the next tile's lin_in right behind the last fc_1 into the other TMEM half (x / net ping-pong)
     int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
 };
 
@@ -415,9 +416,9 @@ __device__ __forceinline__ void add32_convert(uint32_t* v, int h0, int r, uint8_
     }
 }
 template <bool PARITY>
-__device__ __forceinline__ void epilogue_add_y_half(uint32_t tmem, uint8_t* Ahi, uint8_t* Alo, int q, int lane, int j, int h) {
+__device__ __forceinline__ void epilogue_add_y_half(uint32_t tmem, int colx, uint8_t* Ahi, uint8_t* Alo, int q, int lane, int j, int h) {
     const int r = 32 * (q & 1) + lane;
-    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * h + 64 * j);
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(colx + 128 * h + 64 * j);
     const int hb = 256 * h + 128 * (q >> 1) + 64 * j;
     uint32_t va[32], vb[32];
     tmem_ld32_issue(t0, va);
@@ -557,7 +558,7 @@ __device__ __forceinline__ void opnd_warps_join() {
     asm volatile("bar.sync 6, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
 }
 
-#define TS_ROUND 20     // a steady-state round (the first rounds of a launch gather cold Y-map lines from HBM)
+#define TS_ROUND 21     // a steady-state tile (the first rounds of a launch gather cold Y-map lines from HBM); fused launch, 4 views: a warm PRE tile
 #define TS(role, slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && lane == 0) a.dbg_ts[(blockIdx.x * 4 + (role)) * 64 + (slot)] = clock64(); } while (0)
 #define TSH(slot) do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && wwarp == NUM_WORKER_WARPS && lane == 0) a.dbg_ts[(blockIdx.x * 4 + 2) * 64 + (slot)] = clock64(); } while (0)
 #define TSW() do { if (a.dbg_ts && blockIdx.x < 2 && rd == TS_ROUND && wwarp == 0 && lane == 0 && tsn < 64) a.dbg_ts[(blockIdx.x * 4 + 1) * 64 + tsn++] = clock64(); } while (0)
@@ -581,7 +582,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     const uint32_t bar_acc = bar_opnd + 16;                        // accumulators of a GEMM step complete (pair commit)
     const uint32_t bar_acc0 = bar_acc + 8;                         // N tile 0 of the step's accumulator complete (pair commit; before bar_acc)
     const uint32_t bar_afree = bar_acc0 + 8;                       // 8: K block kb of the A operand no longer read (pair commit)
-    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + C::OFF_BARS + 8 * (2 * C::NST + 4 + HID / KBLK));
+    const uint32_t bar_lin0 = bar_afree + 8 * (HID / KBLK);          // lin_in: N tile 0 / the whole step complete.  Its own pair of barriers:
+    const uint32_t bar_lin = bar_lin0 + 8;                          // lin_in of the NEXT tile is issued right behind the last fc_1 (early_lin),
+                                                                   // and two phases of ONE barrier must never complete within a waiter's reach
+    const uint32_t bar_feat = bar_lin + 8;                          // (leader) lin_in features of the next tile in place in both CTAs (helper warps)
+    volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + C::OFF_BARS + 8 * (2 * C::NST + 4 + HID / KBLK + 3));
 
     if ((smem_base & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(a.err, 90); __trap(); }
     const long long clk_start = a.dbg_ts ? clock64() : 0;
@@ -591,6 +596,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         mbar_init(bar_opnd + 8, NUM_WORKER_WARPS + 1);
         mbar_init(bar_acc, 1);
         mbar_init(bar_acc0, 1);
+        mbar_init(bar_lin0, 1);
+        mbar_init(bar_lin, 1);
+        mbar_init(bar_feat, NUM_HELPER_WARPS + 1);
         for (int i = 0; i < HID / KBLK; ++i) mbar_init(bar_afree + 8 * i, 1);
         fence_barrier_init();
     }
@@ -604,6 +612,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t leader_opnd = map_to_cta(bar_opnd, 0);      // + 8 * half
+    const uint32_t leader_feat = map_to_cta(bar_feat, 0);
 
     // both CTAs of a pair run the same number of rounds; CTA tile = 2 * pair_tile + rank
     const long long first = (long long)blockIdx.x, stride = (long long)gridDim.x;
@@ -646,10 +655,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         uint32_t use = 0, oph[2] = {0, 0};
         // the GEMM steps of one tile; cold = no previous PRE tile prepared this one (the whole Y_0 gather follows lin_in),
         // has_next = another PRE tile follows in the pipeline (its early gather consumes the last fc_1's operand releases)
-        auto run_steps = [&](const GemmStep* steps, int n_steps, bool cold, bool has_next, long long rd) {
-            for (int sidx = 0; sidx < n_steps; ++sidx) {
-                GemmStep gs = steps[sidx];
+        uint32_t fph = 0;                        // phases of bar_feat consumed
+        // One GEMM step.  par: TMEM half parity of the tile (x / net swap columns from tile to tile, see early_lin); via_feat: the
+        // operand is the next tile's lin_in features, signalled by the helper warps on bar_feat (not by the workers on bar_opnd)
+        auto issue_step = [&](GemmStep gs, int sidx, bool cold, bool has_next, long long rd, int par, bool via_feat) {
+            {
                 if (gs.release == 3) gs.release = has_next ? 1 : 0;
+                const bool is_lin = gs.release == 2;
+                gs.dst_col = (short)(gs.dst_col ^ (par ? 256 : 0));
                 const uint32_t idesc = make_idesc2(gs.n_width);
                 // K blocks [0, kb_split) K-block-outer over both N tiles; the tail [kb_split, nkb) N-tile-outer: N tile 0 of the
                 // accumulator completes `tail` K blocks early (bar_acc0) and its epilogue half overlaps the n1 tail
@@ -657,8 +670,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 auto wait_half = [&](int kb) {
                     if ((kb & 3) == 0) {
                         const int h = kb >> 2;
-                        mbar_wait(bar_opnd + 8 * h, oph[h] & 1, a.err, 20 + h);
-                        ++oph[h];
+                        if (via_feat) { mbar_wait(bar_feat, fph & 1, a.err, 22); ++fph; }
+                        else { mbar_wait(bar_opnd + 8 * h, oph[h] & 1, a.err, 20 + h); ++oph[h]; }
                         tc_fence_after();
                         TS(0, 4 * sidx + h);
                     }
@@ -711,25 +724,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         if (n2 + 1 == gs.n_tiles && gs.release && leader) umma2_commit_pair(bar_afree + 8 * kb);
                         __syncwarp();
                     }
-                    if (n2 == 0 && leader) umma2_commit_pair(bar_acc0);      // N tile 0 (or the whole of a single-tile step)
+                    if (n2 == 0 && leader) umma2_commit_pair(is_lin ? bar_lin0 : bar_acc0);      // N tile 0 (or the whole of a single-tile step)
                     __syncwarp();
                 }
                 if (leader) {
-                    // lin_in (release == 2) reads K block 0 only; in the first round the gather of the whole Y_0 row set follows it, so
-                    // the other K blocks are released here as well (later rounds gather them during the previous tile's last fc_1)
-                    if (gs.release == 2 && cold) for (int kb = gs.nkb; kb < HID / KBLK; ++kb) umma2_commit_pair(bar_afree + 8 * kb);
-                    umma2_commit_pair(bar_acc);
+                    // lin_in (release == 2) reads K block 0 only; in a cold tile the gather of the whole Y_0 row set follows it, so
+                    // the other K blocks are released here as well (warm tiles gather them during the previous tile's last fc_1)
+                    if (is_lin && cold) for (int kb = gs.nkb; kb < HID / KBLK; ++kb) umma2_commit_pair(bar_afree + 8 * kb);
+                    umma2_commit_pair(is_lin ? bar_lin : bar_acc);
                 }
                 __syncwarp();
                 TS(0, 4 * sidx + 2);
             }
         };
+        // The steps of one tile.  early_lin: lin_in of a warm tile was issued at the end of the previous tile (right behind its last
+        // fc_1, into the TMEM half that tile used for `net`), so the tile starts with its blocks and ends with the next tile's lin_in.
+        auto run_steps = [&](const GemmStep* steps, int n_steps, bool cold, bool has_next, long long rd, int par) {
+            const bool early = a.early_lin && steps[0].release == 2;
+            for (int sidx = (early && !cold) ? 1 : 0; sidx < n_steps; ++sidx) issue_step(steps[sidx], sidx, cold, has_next, rd, par, false);
+            if (early && has_next) issue_step(steps[0], 0, false, false, rd + 1, par ^ 1, true);
+        };
         for (long long rd = 0; rd < n_rounds; ++rd) {
             if constexpr (FUSED) {
-                for (int j = 0; j < a.ppr; ++j) run_steps(a.steps, a.n_steps, j == 0, j + 1 < a.ppr, rd * a.ppr + j);
-                for (int k = 0; k < a.pts; ++k) run_steps(a.steps_post, a.n_steps_post, false, false, -1);
+                for (int j = 0; j < a.ppr; ++j) run_steps(a.steps, a.n_steps, j == 0, j + 1 < a.ppr, rd * a.ppr + j, a.early_lin ? (j & 1) : 0);
+                for (int k = 0; k < a.pts; ++k) run_steps(a.steps_post, a.n_steps_post, false, false, -1, 0);
             } else {
-                run_steps(a.steps, a.n_steps, rd == 0, rd + 1 < n_rounds, rd);
+                run_steps(a.steps, a.n_steps, rd == 0, rd + 1 < n_rounds, rd, (a.early_lin && KIND == KIND_PRE) ? (int)(rd & 1) : 0);
             }
         }
     } else if (warp >= WORKER_WARP0) {
@@ -739,22 +759,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         const bool helper = wwarp >= NUM_WORKER_WARPS;
         const int q = warp & 3, n2 = (wwarp >> 2) & 1;
         const int r = 32 * (q & 1) + lane;
-        uint32_t it = 0, ph0 = 0, ph1 = 0;   // phase counters: bar_acc, bar_afree[0], bar_afree[1..7]
+        uint32_t it = 0, ph0 = 0, ph1 = 0, itl = 0;   // phase counters: bar_acc, bar_afree[0], bar_afree[1..7], bar_lin
         const uint64_t slab_pol = FUSED ? l2_evict_last_policy() : 0;
         (void)ph0; (void)ph1;
         // One PRE tile (64 sample-view rows).  cold: nothing was prepared by a previous tile; has_next: tile_next follows in the
         // pipeline (its taps / features / Y_0 are produced under this tile's last block); pt: running PRE tile count (tap buffer
         // parity); xc_row0 (FUSED): first row of this tile's samples in the CTA's x_c slab.
-        auto pre_tile = [&](long long tile, bool live, bool cold, bool has_next, long long tile_next, long long pt, long long xc_row0) {
+        auto pre_tile = [&](long long tile, bool live, bool cold, bool has_next, long long tile_next, long long pt, long long xc_row0, int par) {
             // Tile pipeline (steady state, !cold): the taps and the lin_in features of this tile, and the Y_0 staging of
             // K blocks 1..7, were produced during the previous tile's last block; its lin_in was handed off after that tile's combine.
             int tsn = 0; (void)tsn;
             const long long rd = pt; (void)rd;
             if (a.dbg_ts && blockIdx.x < 4 && wwarp == 0 && lane == 0) a.dbg_ts[512 + blockIdx.x * 512 + (pt < 511 ? pt : 511)] = clock64();
-            const Tap* tp = taps + (pt & 1) * ROWS;
+            Tap* tp = taps + (pt & 1) * ROWS;
             Tap* tn = taps + ((pt + 1) & 1) * ROWS;
+            // TMEM halves of this tile: with early_lin the residual x and the fc_0 output swap columns from tile to tile (the next
+            // tile's lin_in is written into this tile's `net` half while this tile's x is still being combined)
+            const int colX = par ? COL_NET : COL_X, colNET = par ? COL_X : COL_NET;
             if (cold) {
-                prep_rows<PARITY, NUM_OPND_WARPS * 32 / 64, true, true>(a, tile, wt, Ahi, Alo, taps);
+                prep_rows<PARITY, NUM_OPND_WARPS * 32 / 64, true, true>(a, tile, wt, Ahi, Alo, tp);
                 opnd_warps_join();
                 if (!helper) worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                   // -> lin_in (K block 0 only)
             }
@@ -773,7 +796,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 // Helpers never wait on bar_acc in this kernel: they are gated by bar_afree alone.  (A helper that finishes a late
                 // gather could reach a bar_acc wait after the barrier has already completed its NEXT phase -- lin_in of the next
                 // tile is short -- and a parity wait that is one phase late blocks for good.)
-                if (!helper) mbar_wait(bar_acc0, it & 1, a.err, 40);                                               // x, N tile 0 (hidden 0..255) complete
+                if (!helper) {                                                                                     // x, N tile 0 (hidden 0..255) complete
+                    if (b == 0) mbar_wait(bar_lin0, itl & 1, a.err, 40); else mbar_wait(bar_acc0, it & 1, a.err, 40);
+                }
                 TSW();
                 tc_fence_after();
                 if (helper) {
@@ -785,23 +810,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     }
                 } else {
                     asm volatile("bar.sync 5, %0;" ::"n"(NUM_WORKERS) : "memory");                                  // staging of K blocks 0..4 complete
-                    if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 0);
+                    if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, colX, Ahi, Alo, q, lane, n2, 0);
                     TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 0..3
                     asm volatile("bar.sync 3, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
-                    mbar_wait(bar_acc, it & 1, a.err, 41); ++it;                                                    // x complete
+                    if (b == 0) { mbar_wait(bar_lin, itl & 1, a.err, 41); ++itl; }                                  // x complete
+                    else { mbar_wait(bar_acc, it & 1, a.err, 41); ++it; }
                     tc_fence_after();
-                    if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, Ahi, Alo, q, lane, n2, 1);
+                    if (!(a.dbg_skip & 2)) epilogue_add_y_half<PARITY>(tmem, colX, Ahi, Alo, q, lane, n2, 1);
                     TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_0[b], K blocks 4..7
                 }
                 if (!helper) {
                     mbar_wait(bar_acc0, it & 1, a.err, 42); TSW();                                                  // net, N tile 0
                     tc_fence_after();
                     const float* b0 = a.bias + (size_t)(a.n_blocks + b) * HID;
-                    if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 0);
+                    if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, colNET, b0, Ahi, Alo, q, lane, n2, 0);
                     TSW(); worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 0..3
                     mbar_wait(bar_acc, it & 1, a.err, 39); ++it;                                                    // net complete
                     tc_fence_after();
-                    if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
+                    if (!(a.dbg_skip & 2)) epilogue_half<PARITY>(tmem, colNET, b0, Ahi, Alo, q, lane, n2, 1);
                     TSW(); worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                     // -> fc_1[b], K blocks 4..7
                 }
                 if (last && has_next) {
@@ -814,15 +840,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         prep_rows<PARITY, NUM_HELPER_WARPS * 32 / 64, false, true>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
                         TSH(2);
                         fence_proxy_async();
-                        asm volatile("bar.arrive 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                    // features in place
+                        if (a.early_lin) {
+                            // features in place -> straight to the issuer (leader's bar_feat; the peer's helpers join first and
+                            // send ONE remote arrive, like worker_arrive)
+                            const int hw = wwarp - NUM_WORKER_WARPS;
+                            if (is_leader_cta) {
+                                __syncwarp();
+                                if (lane == 0) tc::mbar_arrive(bar_feat);
+                            } else if (hw == 0) {
+                                asm volatile("bar.sync 11, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");
+                                if (lane == 0) mbar_arrive_remote(leader_feat);
+                            } else {
+                                asm volatile("bar.arrive 11, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");
+                            }
+                        } else {
+                            asm volatile("bar.arrive 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                // features in place
+                        }
                     } else {
                         asm volatile("bar.sync 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                      // next taps in place
                     }
                     gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.early_worker_kb_hi);
                     if (helper) TSH(3); else TSW();
-                    // workers consume K block 0's phase too (the helpers did above -- and must NOT wait on it again here: by the time
-                    // they finish their late K blocks, lin_in of the next tile may already have completed the barrier's next phase)
-                    if (!helper) mbar_wait(bar_afree, ph0 & 1, a.err, 48);
+                    // K block 0's phase (released by this last fc_1, consumed by the helpers above) is only COUNTED here, never waited
+                    // for: by the time a warp gets here, lin_in of the next tile may already have completed the barrier's NEXT phase
+                    // (with early_lin it does not depend on the workers at all), and a parity wait that is one phase late blocks for
+                    // good.  Skipping is safe: every warp's next wait on bar_afree[0] is for lin_in's release, and the phase after
+                    // that needs all of them (fc_1[0] of the next tile).
                     ++ph0; ++ph1;
                 }
             }
@@ -847,7 +890,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     tc_fence_after();
                 }
                 uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * nt + 32 * c32), v);
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(colX + 128 * nt + 32 * c32), v);
                 const int h0 = 256 * nt + 128 * (q >> 1) + 32 * c32;
                 switch (a.NV) {
                     case 1: combine_store<1>(v, cb, h0, lane, dst_sample, wr, a.NV_real, slab_pol); break;
@@ -861,7 +904,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             if (!helper) ++it;
             tc_fence_before();
             TSW();
-            if (has_next && !helper) {
+            if (has_next && !helper && !a.early_lin) {
                 asm volatile("bar.sync 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                              // next tile's features in place
                 TSW();
                 worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                                // X read out -> lin_in of the next tile
@@ -979,14 +1022,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             } else if constexpr (KIND == KIND_PRE) {
                 long long tile_next = first + (rd + 1) * stride;
                 if (tile_next >= a.n_tiles) tile_next = a.n_tiles - 1;
-                pre_tile(tile, live, rd == 0, rd + 1 < n_rounds, tile_next, rd, 0);
+                pre_tile(tile, live, rd == 0, rd + 1 < n_rounds, tile_next, rd, 0, a.early_lin ? (int)(rd & 1) : 0);
             } else if constexpr (KIND == KIND_POST) {
                 post_tile(tile, live, a.bias, a.n_blocks, 0);
             } else {
                 // FUSED: a.n_tiles counts rounds of 64 * pts samples; PRE tile j covers samples [64 * pts * tile + j * spv, + spv)
                 const long long slab = (long long)blockIdx.x * ROWS * a.pts;
                 for (int j = 0; j < a.ppr; ++j)
-                    pre_tile(tile * a.ppr + j, live, j == 0, j + 1 < a.ppr, tile * a.ppr + j + 1, rd * a.ppr + j, slab + (long long)j * a.spv);
+                    pre_tile(tile * a.ppr + j, live, j == 0, j + 1 < a.ppr, tile * a.ppr + j + 1, rd * a.ppr + j, slab + (long long)j * a.spv,
+                             a.early_lin ? (j & 1) : 0);
                 for (int k = 0; k < a.pts; ++k) post_tile(tile * a.pts + k, live, a.bias_post, a.n_blocks_post, slab + (long long)k * ROWS);
             }
         }
@@ -1182,6 +1226,7 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     // workers gather the K blocks that are released in the K-block-outer part of the running GEMM, helpers those of its tail
     pre.worker_kb_hi = t.tail_kb > 0 ? HID / KBLK - 1 - t.tail_kb : 4;
     pre.early_worker_kb_hi = t.early_split > 0 ? t.early_split : pre.worker_kb_hi;
+    pre.early_lin = t.early_lin;
     static long long* dbg_ts = nullptr;      // device memory (managed memory would page-fault inside the kernel and distort the timeline)
     if ((t.dbg_skip & 512) && !dbg_ts) TCK(cudaMalloc((void**)&dbg_ts, 4096 * sizeof(long long)));
     if (t.dbg_skip & 512) TCK(cudaMemsetAsync(dbg_ts, 0, 4096 * sizeof(long long), st));

@@ -370,7 +370,8 @@ def test_other_config_shapes_forward(name, cfg):
 
 @pytest.mark.parametrize("NV,SB,K,nr", [(1, 1, 8, 1), (1, 2, 16, 37), (2, 1, 40, 300), (4, 1, 64, 1000), (4, 2, 24, 2500),
                                         (8, 1, 16, 1200), (8, 1, 64, 3000), (2, 2, 64, 4100), (4, 1, 128, 4096),
-                                        (3, 1, 20, 700), (6, 2, 16, 900)])      # view counts that are not powers of two: padded rows
+                                        (3, 1, 20, 700), (6, 2, 16, 900),       # view counts that are not powers of two: padded rows
+                                        (1, 1, 64, 1500)])                      # one view, many rounds per CTA: every tile is a cold one
 def test_pair_kernel_pipeline_shape_sweep(NV, SB, K, nr):
     """The software pipeline of the CTA-pair kernel (per-K-block release barriers, cross-tile hand-off, helper warps)
     over many tile counts -- 1 tile to >10 rounds per CTA, live and padded last rounds, 1..8 views: parity mode must agree
@@ -413,6 +414,12 @@ def test_pair_kernel_pipeline_shape_sweep(NV, SB, K, nr):
         ctx.set_option("tail_kb", tail)
         _, rgb_t, d_t = ctx.composite(rays, z, True, 1, want_weights=False)
         assert torch.equal(rgb_t, rgb_p) and torch.equal(d_t, d_p), "tail_kb=%d changes the result" % tail
+    ctx.set_option("tail_kb", 3)
+    for early, fused in ((1, 1), (1, 0), (0, 0), (0, 1)):                   # next tile's lin_in behind the last fc_1 (TMEM half ping-pong)
+        ctx.set_option("early_lin", early)
+        ctx.set_option("fused", fused)
+        _, rgb_t, d_t = ctx.composite(rays, z, True, 1, want_weights=False)
+        assert torch.equal(rgb_t, rgb_p) and torch.equal(d_t, d_p), "early_lin=%d fused=%d changes the result" % (early, fused)
 
 
 @pytest.mark.parametrize("backward_tc", [1, 0], ids=["tcgen05", "fp32_cuda_cores"])

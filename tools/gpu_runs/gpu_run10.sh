@@ -1,10 +1,12 @@
+# early_lin validation: gate tests (the sweep toggles the option in both launch modes), then the whole parity file with the option on, bench both
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -6
-timeout 600 python bench.py > gpurun_out/r2j_bench_default.json 2> gpurun_out/r2j_bench_default.err; python -c "
-import json;d=json.load(open('gpurun_out/r2j_bench_default.json'));print(d['value'],d['e2e'],d['roofline']['frac'],d['roofline']['stage_ms_per_step'],d['clocks'],d['gpu_launches'],d['parity'],d['cpu_baseline']['value'],d['gpu_eager_baseline'])"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlp_pair_kernel -s 1 -c 1 -o gpurun_out/r2j_fused_parity python tools/profile_run.py parity 8192 2 > gpurun_out/r2j_ncu_full.log 2>&1; tail -2 gpurun_out/r2j_ncu_full.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2j_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2j_ncu_list.log 2>&1
-timeout 900 python bench.py --workload train256 --steps 2 --warmup 1 > gpurun_out/r2j_bench_train256.json 2> gpurun_out/r2j_bench_train256.err; cat gpurun_out/r2j_bench_train256.json | cut -c1-900; tail -3 gpurun_out/r2j_bench_train256.err
-timeout 300 python bench.py --mode fast --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2j_bench_fast.json 2>/dev/null; python -c "
-import json;d=json.load(open('gpurun_out/r2j_bench_fast.json'));print('fast',d['value'],d['roofline']['frac'],d['parity'])"
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "sweep" 2>&1 | tail -5
+export DINER_TC_EARLY_LIN=1
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+unset DINER_TC_EARLY_LIN
+for e in 0 1 0 1; do
+  DINER_TC_EARLY_LIN=$e timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>/dev/null | grep "^{" > gpurun_out/r2v_bench_early$e.json
+  python -c "
+import json;d=json.load(open('gpurun_out/r2v_bench_early$e.json'));print('early',$e,d['value'],d['ms_per_step'],d['roofline']['frac'],d['clocks'])"
+done
+DINER_TC_EARLY_LIN=1 DINER_TC_DBG_SKIP=512 timeout 300 python tools/profile_run.py parity 8192 1 2>&1 | tail -40 > gpurun_out/r2v_timeline_early1.txt
