@@ -106,7 +106,7 @@ class Context:
         self.handle = h
         self._keep = []
         for key, env in (("ray_image_width", "DINER_RAY_IMAGE_WIDTH"), ("backward_tc", "DINER_B200_BACKWARD_TC"), ("fused", "DINER_TC_FUSED"), ("post_tiles", "DINER_TC_POST_TILES"), ("tail_kb", "DINER_TC_TAIL_KB"), ("sub_batch", "DINER_TC_SUB_BATCH"),
-                         ("dbg_skip", "DINER_TC_DBG_SKIP"), ("early_split", "DINER_TC_EARLY_SPLIT"), ("early_lin", "DINER_TC_EARLY_LIN")):
+                         ("dbg_skip", "DINER_TC_DBG_SKIP"), ("early_split", "DINER_TC_EARLY_SPLIT"), ("early_lin", "DINER_TC_EARLY_LIN"), ("warm_rounds", "DINER_TC_WARM_ROUNDS")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))
 

@@ -525,6 +525,8 @@ extern "C" int diner_set_option(diner_ctx* c, const char* key, long long value) 
     } else if (!strcmp(key, "tail_kb")) {
         if (value < 0 || value > 4) return fail(DINER_E_INVALID, "tail_kb must be in [0,4]");
         c->tc.tail_kb = (int)value;
+    } else if (!strcmp(key, "warm_rounds")) {
+        c->tc.warm_rounds = value != 0;
     } else if (!strcmp(key, "early_lin")) {
         c->tc.early_lin = value != 0;
     } else if (!strcmp(key, "early_split")) {

@@ -275,7 +275,7 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
     const int kbz = m.d_latent / KBLK, kbh = HID / KBLK;
     t.n_pre = n_pre; t.n_post = n_post;
     t.pairs_pre = MT * 1 + n_pre * (MT * kbz + 2 * MT * kbh);
-    t.pairs_post = n_post * 2 * MT * kbh + 2 * kbh;       // lin_out packed as 2 M-tiles (the second is zeros, for the pair kernel)
+    t.pairs_post = n_post * 2 * MT * kbh;                 // (lin_out is not packed: the POST epilogue computes it from the fp32 weights)
     const size_t bytes = (size_t)(t.pairs_pre + t.pairs_post) * 2 * WTILE_BYTES;
     if (bytes > t.wpack_bytes) {
         if (t.wpack) cudaFree(t.wpack);
@@ -305,7 +305,6 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
         TCK(pack(m.w_fc0[b], HID, HID, kbh, MT));
         TCK(pack(m.w_fc1[b], HID, HID, kbh, MT));
     }
-    TCK(pack(m.w_out, m.d_out, HID, kbh, 2));
     t.bias_post_off = (size_t)(2 * DINER_MAX_BLOCKS + 2) * HID;
     t.bias_pair_off = (size_t)(4 * DINER_MAX_BLOCKS + 4) * HID;
     pack_bias_kernel<<<(HID + 127) / 128, 128, 0, st>>>(m, t.bias, t.bias + t.bias_post_off, t.bias + t.bias_pair_off);
@@ -318,7 +317,6 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
         t.wmap_ok = false;
-        t.wmap_small_ok = false;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
             cuuint64_t gdim[2] = {64, (cuuint64_t)(t.pairs_pre + t.pairs_post) * 2 * 128};
             cuuint64_t gstr[1] = {128};
@@ -328,11 +326,6 @@ cudaError_t tc_pack_weights(TcState& t, const MlpDev& m, cudaStream_t st) {
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             t.wmap_ok = (r == CUDA_SUCCESS);
-            cuuint32_t box16[2] = {64, 16};
-            r = ((EncodeFn)fn)(&t.wmap_small, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, t.wpack, gdim, gstr, box16, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            t.wmap_small_ok = t.wmap_ok && (r == CUDA_SUCCESS);
         }
         (void)cudaGetLastError();
     }

@@ -29,8 +29,7 @@ struct TcState {
     float ms_zmap = 0.f;          // device time of the last Y-map build (timing enabled)
     CUtensorMap wmap;             // 2-D view of wpack: rows of 128 B, box = one 16 KiB tile (pair kernel: cta_group::2 TMA)
     bool wmap_ok = false;
-    CUtensorMap wmap_small;       // same buffer, box = first 16 rows of a tile (2 KiB): lin_out in the pair kernel
-    bool wmap_small_ok = false;
+    int warm_rounds = 1;          // fused launch: next round's first PRE tile prepared under the POST tile's last fc_1 (implies early_lin)
     int early_lin = 0;            // pair kernel PRE tiles: next tile's lin_in issued behind the last fc_1 into the other TMEM half
     int early_split = 0;          // pair kernel PRE: worker/helper split of the next tile's early Y_0 gather (0 = same as inside a tile)
     int dbg_skip = 0;             // profiling experiments (pair kernel PRE): see tc2::Args::dbg_skip

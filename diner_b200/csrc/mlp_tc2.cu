@@ -18,7 +18,8 @@
 //
 // Row-major orientation: the epilogue thread owns one ROW (sample-view / sample) and 32 consecutive hidden units per
 // TMEM load, writes 16-byte K-major chunks into the next layer's A operand; the mean over views is a shuffle over
-// adjacent lanes; lin_out is an N=32 MMA whose 4 valid outputs land in the row's own thread.
+// adjacent lanes; lin_out (4 outputs) runs on the CUDA cores in the POST epilogue: 512 FMAs per thread on the last fc_1's
+// accumulator, partial sums of the four warps that hold a row added in a fixed order through shared memory.
 //
 // lin_z is hoisted out of the per-sample work: grid_sample(bilinear) and lin_z are both linear, so
 //   lin_z[b](bilinear(latent, uv)) == bilinear(lin_z[b](latent), uv)      (the four tap weights sum to 1)
@@ -33,7 +34,11 @@
 //     K block by K block behind bar_afree while fc_1 of the previous block still runs (loads are issued before the wait);
 //   * epilogues run in two halves (K blocks 0..3 / 4..7), one operand barrier each, so the next GEMM starts on half 0;
 //   * across tiles: under the last fc_1 the helper warps compute the next tile's taps and lin_in features and everyone gathers
-//     its Y_0 (K blocks 1..7); lin_in of the next tile is handed off right after the view-combine.
+//     its Y_0 (K blocks 1..7); lin_in of the next tile is handed off right after the view-combine -- or (early_lin) issued
+//     straight behind that fc_1 into the OTHER TMEM half: x and net swap halves from tile to tile, so the next tile's lin_in does
+//     not have to wait for this tile's x to be combined;
+//   * across rounds (warm_rounds, default): the POST tile's last fc_1 hands off to the next round's first PRE tile in the same way
+//     (lin_out off the tensor pipe is what frees the operand buffers for it), so only the first tile of a launch starts cold;
 //   * accumulator halves: the first epilogue half reads only N tile 0 of the accumulator (hidden units 0..255 = K blocks 0..3 of
 //     the next layer), so the last `tail` K blocks of every full-width step are issued N-TILE-OUTER -- (kb, n0) for the tail,
 //     commit bar_acc0, then (kb, n1), commit bar_acc -- and that epilogue half runs under the n1 tail of the same GEMM.  It writes
@@ -78,8 +83,6 @@ constexpr int ROWS = 64;                    // rows per CTA (128 per pair)
 constexpr int HID = 512;
 constexpr int KBLK = 64;
 constexpr int WTILE_BYTES = 128 * KBLK * 2; // 16 KiB: 128 hidden rows x 64 k, K-major SWIZZLE_128B (same packing as mlp_tc.cu)
-constexpr int SMALL_TILE_BYTES = 16 * KBLK * 2; // 2 KiB: the first 16 rows of a weight tile (lin_out)
-constexpr int TILE_SMALL = 1 << 30;             // tile-table flag: load only SMALL_TILE_BYTES of this tile
 constexpr int ACT_KB_BYTES = ROWS * 128;    // 8 KiB per 64-wide K block of the activation operand
 constexpr int ACT_BYTES = ACT_KB_BYTES * (HID / KBLK);   // 64 KiB per fp16 copy
 constexpr int NUM_THREADS = 512;
@@ -104,7 +107,7 @@ struct Tap {
 struct GemmStep {
     short nkb;         // K blocks of 64
     short n_tiles;     // N tiles (of n_width hidden units) = weight tiles per CTA per K block
-    short n_width;     // UMMA N: 256, or 32 for lin_out
+    short n_width;     // UMMA N: 256
     short dst_col;     // TMEM column base
     short accumulate;
     short release;     // commit the per-K-block "A operand free" barriers (a gather into A overlaps / follows the step); 2 = lin_in;
@@ -114,7 +117,6 @@ struct GemmStep {
 
 struct Args {
     CUtensorMap wmap;           // packed weight stream as rows of 128 B; one box = one 16 KiB tile
-    CUtensorMap wmap_small;     // same stream, box = the first 16 rows (2 KiB) of a tile: lin_out (N = 32 over the pair) needs no more
     SceneDev s;
     QueryArgs q;
     const uint8_t* wstream;     // packed weight tiles (16 KiB units), shared with mlp_tc.cu's packing
@@ -144,6 +146,9 @@ struct Args {
                                 // (the Y-map lines gathered by neighbouring rays stay in L2); 0 = process in the caller's order
     int early_worker_kb_hi;     // next-tile Y_0 gather under the last fc_1: K blocks 1..this on the workers, the rest on the helpers
     int worker_kb_hi;           // Y_b gather inside a tile: K blocks 0..this on the workers (released before the N-outer tail), the rest on the helpers
+    const float* w_out;         // lin_out weights, fp32 [4][512] (the output layer runs on the CUDA cores in the POST epilogue)
+    const float* b_out;
+    int warm_rounds;            // FUSED: the first PRE tile of the next round is prepared under the POST tile's last fc_1 (needs early_lin, even ppr)
     int early_lin;              // PRE tiles: issue the next tile's lin_in right behind the last fc_1 into the other TMEM half (x / net ping-pong)
     int dbg_skip;               // profiling experiments only: 1 skip gather, 2 skip epilogues, 4 skip prep, 8 skip MMA issue
 };
@@ -249,6 +254,36 @@ __device__ __forceinline__ void epilogue_half(uint32_t tmem, int colbase, const 
     tmem_ld_wait();
     convert32<PARITY>(va, bias, hb, r, Ahi, Alo);
     convert32<PARITY>(vb, bias, hb + 32, r, Ahi, Alo);
+}
+
+// Output layer on the CUDA cores (POST epilogue): this thread's 64 columns of x in half h -> relu(x) . W_out[0..3], accumulated
+// in column order into acc.  (The layer is 4 outputs wide: as a GEMM step it kept the whole A operand and the tensor pipe busy for
+// ~1/30 of a tile's work and put a staging + hand-off between the last fc_1 and the result; as 512 FMAs per thread it leaves the
+// operand buffers free for the next round's first PRE tile as soon as the last fc_1 has read them.)
+__device__ __forceinline__ void lin_out_dot32(const uint32_t* v, const float* __restrict__ bias, const float* __restrict__ w_out, int h0, float (&acc)[4]) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 b = __ldg((const float4*)(bias + h0 + 4 * c4));
+        float x[4];
+        x[0] = fmaxf(fmaf(__uint_as_float(v[4 * c4 + 0]), W_INV, b.x), 0.0f); x[1] = fmaxf(fmaf(__uint_as_float(v[4 * c4 + 1]), W_INV, b.y), 0.0f);
+        x[2] = fmaxf(fmaf(__uint_as_float(v[4 * c4 + 2]), W_INV, b.z), 0.0f); x[3] = fmaxf(fmaf(__uint_as_float(v[4 * c4 + 3]), W_INV, b.w), 0.0f);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const float4 w = __ldg((const float4*)(w_out + o * HID + h0 + 4 * c4));
+            acc[o] = fmaf(x[3], w.w, fmaf(x[2], w.z, fmaf(x[1], w.y, fmaf(x[0], w.x, acc[o]))));
+        }
+    }
+}
+__device__ __forceinline__ void lin_out_half(uint32_t tmem, int colx, const float* __restrict__ bias, const float* __restrict__ w_out, int q, int lane,
+                                             int j, int h, float (&acc)[4]) {
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(colx + 128 * h + 64 * j);
+    const int hb = 256 * h + 128 * (q >> 1) + 64 * j;
+    uint32_t va[32], vb[32];
+    tmem_ld32_issue(t0, va);
+    tmem_ld32_issue(t0 + 32, vb);
+    tmem_ld_wait();
+    lin_out_dot32(va, bias, w_out, hb, acc);
+    lin_out_dot32(vb, bias, w_out, hb + 32, acc);
 }
 
 // PRE prep: PARTS threads per row (wt = row + 64 * part).  Camera transform, projection, nearest depth; TAPS: the row's
@@ -638,11 +673,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 if (leader) {
                     const int tix = (!FUSED || t < a.ppr * a.uses_per_tile) ? __ldg(table + t % a.uses_per_tile)
                                                                             : __ldg(table_post + (t - a.ppr * a.uses_per_tile) % a.uses_post);
-                    const bool small = (tix & TILE_SMALL) != 0;          // lin_out: only the first 16 rows of the tile are read
-                    const int row = (tix & (TILE_SMALL - 1)) * 128;
-                    if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, small ? 2 * SMALL_TILE_BYTES : 2 * WTILE_BYTES);
+                    const int row = tix * 128;
+                    if (is_leader_cta) mbar_arrive_expect_tx(bar_full + 8 * st, 2 * WTILE_BYTES);
                     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(smem_base + st * WTILE_BYTES), "l"(small ? &a.wmap_small : &a.wmap), "r"(0), "r"(row), "r"(leader_full + 8 * st) : "memory");
+                                 ::"r"(smem_base + st * WTILE_BYTES), "l"(&a.wmap), "r"(0), "r"(row), "r"(leader_full + 8 * st) : "memory");
                 }
                 __syncwarp();
             }
@@ -746,8 +780,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         };
         for (long long rd = 0; rd < n_rounds; ++rd) {
             if constexpr (FUSED) {
-                for (int j = 0; j < a.ppr; ++j) run_steps(a.steps, a.n_steps, j == 0, j + 1 < a.ppr, rd * a.ppr + j, a.early_lin ? (j & 1) : 0);
-                for (int k = 0; k < a.pts; ++k) run_steps(a.steps_post, a.n_steps_post, false, false, -1, 0);
+                for (int j = 0; j < a.ppr; ++j)
+                    run_steps(a.steps, a.n_steps, j == 0 && (rd == 0 || !a.warm_rounds), j + 1 < a.ppr, rd * a.ppr + j,
+                              a.warm_rounds ? ((j + 1) & 1) : a.early_lin ? (j & 1) : 0);
+                for (int k = 0; k < a.pts; ++k) {
+                    // warm_rounds: the last fc_1 of the round's last POST tile releases its K blocks to the next round's first PRE
+                    // tile, whose lin_in (a.steps[0]) follows it into TMEM half 1
+                    const bool warm_next = a.warm_rounds && k + 1 == a.pts && rd + 1 < n_rounds;
+                    run_steps(a.steps_post, a.n_steps_post, false, warm_next, -1, 0);
+                    if (warm_next) issue_step(a.steps[0], 0, false, false, (rd + 1) * a.ppr, 1, true);
+                }
             } else {
                 run_steps(a.steps, a.n_steps, rd == 0, rd + 1 < n_rounds, rd, (a.early_lin && KIND == KIND_PRE) ? (int)(rd & 1) : 0);
             }
@@ -762,6 +804,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
         uint32_t it = 0, ph0 = 0, ph1 = 0, itl = 0;   // phase counters: bar_acc, bar_afree[0], bar_afree[1..7], bar_lin
         const uint64_t slab_pol = FUSED ? l2_evict_last_policy() : 0;
         (void)ph0; (void)ph1;
+        // helpers: next tile's lin_in features in place -> straight to the issuer (leader's bar_feat; the peer's helpers join first
+        // and send ONE remote arrive, like worker_arrive)
+        auto feat_arrive = [&]() {
+            const int hw = wwarp - NUM_WORKER_WARPS;
+            if (is_leader_cta) {
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(bar_feat);
+            } else if (hw == 0) {
+                asm volatile("bar.sync 11, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");
+                if (lane == 0) mbar_arrive_remote(leader_feat);
+            } else {
+                asm volatile("bar.arrive 11, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");
+            }
+        };
         // One PRE tile (64 sample-view rows).  cold: nothing was prepared by a previous tile; has_next: tile_next follows in the
         // pipeline (its taps / features / Y_0 are produced under this tile's last block); pt: running PRE tile count (tap buffer
         // parity); xc_row0 (FUSED): first row of this tile's samples in the CTA's x_c slab.
@@ -834,6 +890,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     // next tile, under the last fc_1: lin_in features into K block 0 as soon as fc_1 has consumed it (helpers),
                     // Y_0 staging of K blocks 1..7 as they are released (everyone)
                     if (helper) {
+                        // (computing the features BEFORE this wait and only storing them after it was measured: slower -- the sin / cos
+                        // work then runs under the last block's epilogues and takes issue slots from the worker warps that the MMA waits for)
                         TSH(0);
                         mbar_wait(bar_afree, ph0 & 1, a.err, 47);
                         TSH(1);
@@ -841,18 +899,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                         TSH(2);
                         fence_proxy_async();
                         if (a.early_lin) {
-                            // features in place -> straight to the issuer (leader's bar_feat; the peer's helpers join first and
-                            // send ONE remote arrive, like worker_arrive)
-                            const int hw = wwarp - NUM_WORKER_WARPS;
-                            if (is_leader_cta) {
-                                __syncwarp();
-                                if (lane == 0) tc::mbar_arrive(bar_feat);
-                            } else if (hw == 0) {
-                                asm volatile("bar.sync 11, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");
-                                if (lane == 0) mbar_arrive_remote(leader_feat);
-                            } else {
-                                asm volatile("bar.arrive 11, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");
-                            }
+                            feat_arrive();
                         } else {
                             asm volatile("bar.arrive 8, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                // features in place
                         }
@@ -917,8 +964,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 asm volatile("bar.sync 10, %0;" ::"n"(NUM_WORKERS) : "memory");
             }
         };
-        // One POST tile (64 samples): remaining blocks + lin_out on the view-combined activations.
-        auto post_tile = [&](long long tile, bool live, const float* bias, int n_blocks, long long xc_row0) {
+        // One POST tile (64 samples): remaining blocks + lin_out on the view-combined activations.  has_next (FUSED, warm_rounds): the
+        // PRE tile tile_next (running PRE tile count pt_next) follows; its taps / features / Y_0 staging are produced under this
+        // tile's last fc_1 exactly as under a PRE tile's, and its lin_in is issued behind that fc_1 into this tile's `net` half.
+        auto post_tile = [&](long long tile, bool live, const float* bias, int n_blocks, long long xc_row0, bool has_next, long long tile_next,
+                             long long pt_next) {
+            Tap* tn = taps + (pt_next & 1) * ROWS;
+            float4* red = (float4*)(taps + ((pt_next + 1) & 1) * ROWS);       // the other tap buffer is dead during a POST tile: lin_out partial sums
             // load x_c: W_SCALE * x_c -> TMEM X (the residual the fc_1 steps accumulate onto), relu(x_c) -> A operand
             long long smp = FUSED ? xc_row0 + r : tile * ROWS + r;          // row of the CTA's slab (FUSED) / sample of the sub-batch
             if (!FUSED && smp >= a.n_samples) smp = a.n_samples - 1;
@@ -951,6 +1003,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
             }
             for (int b = 0; b < n_blocks; ++b) {
+                const bool last = b + 1 == n_blocks;
+                if (helper && last && has_next) {    // taps of the next PRE tile (the helpers have nothing else to do in a POST tile)
+                    if (wt - NUM_WORKERS < ROWS) prep_rows<PARITY, 1, true, false>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                    asm volatile("bar.sync 9, %0;" ::"n"(NUM_HELPER_WARPS * 32) : "memory");
+                    asm volatile("bar.arrive 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+                }
                 if (!helper) {
                     const float* b0 = bias + (size_t)(n_blocks + 1 + b) * HID;
                     mbar_wait(bar_acc0, it & 1, a.err, 50);                                                         // net, N tile 0
@@ -961,36 +1019,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     tc_fence_after();
                     epilogue_half<PARITY>(tmem, COL_NET, b0, Ahi, Alo, q, lane, n2, 1);
                     worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                    const float* b1 = bias + (size_t)(b + 1) * HID;
-                    mbar_wait(bar_acc0, it & 1, a.err, 51);                                                         // x, N tile 0
-                    tc_fence_after();
-                    epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
-                    worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                            // -> next fc_0 / lin_out
-                    mbar_wait(bar_acc, it & 1, a.err, 54); ++it;
-                    tc_fence_after();
-                    epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
-                    worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                }
+                if (!last) {
+                    if (!helper) {
+                        const float* b1 = bias + (size_t)(b + 1) * HID;
+                        mbar_wait(bar_acc0, it & 1, a.err, 51);                                                     // x, N tile 0
+                        tc_fence_after();
+                        epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 0);
+                        worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                        // -> next fc_0
+                        mbar_wait(bar_acc, it & 1, a.err, 54); ++it;
+                        tc_fence_after();
+                        epilogue_half<PARITY>(tmem, COL_X, b1, Ahi, Alo, q, lane, n2, 1);
+                        worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
+                    }
+                } else if (has_next) {
+                    // under the last fc_1: the next PRE tile's lin_in features (helpers, K block 0 once fc_1 has read it) and its
+                    // Y_0 staging of K blocks 1..7 as they are released (everyone) -- the same hand-off as between two PRE tiles
+                    if (helper) {
+                        mbar_wait(bar_afree, ph0 & 1, a.err, 56);
+                        prep_rows<PARITY, NUM_HELPER_WARPS * 32 / 64, false, true>(a, tile_next, wt - NUM_WORKERS, Ahi, Alo, tn);
+                        fence_proxy_async();
+                        feat_arrive();
+                    } else {
+                        asm volatile("bar.sync 7, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");                      // next taps in place
+                    }
+                    gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tn, 1, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.early_worker_kb_hi);
+                    ++ph0; ++ph1;                                                                                   // (K block 0: counted, see pre_tile)
                 }
             }
-            if (!helper) {                                                   // lin_out (N=32): outputs 0..3 in columns COL_NET..+3, lanes 0..63
+            // lin_out on the last fc_1's accumulator, half by half as it completes; x = acc * W_INV + b_fc1[last] like every epilogue
+            if (!helper) {
+                const float* b1 = bias + (size_t)n_blocks * HID;
+                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 mbar_wait(bar_acc0, it & 1, a.err, 55);
+                tc_fence_after();
+                lin_out_half(tmem, COL_X, b1, a.w_out, q, lane, n2, 0, acc);
                 mbar_wait(bar_acc, it & 1, a.err, 52); ++it;
-            }
-            tc_fence_after();
-            if (!helper && q < 2 && n2 == 0) {
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)COL_NET, v);
-                const long long s_loc = tile * ROWS + r;
-                if (live && s_loc < a.n_samples) {
-                    const float4 bo = __ldg((const float4*)(bias + (size_t)(2 * n_blocks + 1) * HID));
-                    const float x0 = fmaf(__uint_as_float(v[0]), W_INV, bo.x), x1 = fmaf(__uint_as_float(v[1]), W_INV, bo.y);
-                    const float x2 = fmaf(__uint_as_float(v[2]), W_INV, bo.z), x3 = fmaf(__uint_as_float(v[3]), W_INV, bo.w);
-                    ((float4*)a.out)[map_sample(a, a.s_begin + s_loc)] = make_float4(1.0f / (1.0f + expf(-x0)), 1.0f / (1.0f + expf(-x1)),
-                                                                     1.0f / (1.0f + expf(-x2)), fmaxf(x3, 0.0f));
+                tc_fence_after();
+                lin_out_half(tmem, COL_X, b1, a.w_out, q, lane, n2, 1, acc);
+                // the four warps that hold a row (TMEM lane halves x N-tile column split) add up in a fixed order through shared memory
+                const int cls = 2 * (q >> 1) + n2;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    if (cls == c) {
+                        float4 s = c ? red[r] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        s.x += acc[0]; s.y += acc[1]; s.z += acc[2]; s.w += acc[3];
+                        if (c < 3) red[r] = s;
+                        else {
+                            const long long s_loc = tile * ROWS + r;
+                            if (live && s_loc < a.n_samples) {
+                                const float4 bo = __ldg((const float4*)a.b_out);
+                                const float x0 = s.x + bo.x, x1 = s.y + bo.y, x2 = s.z + bo.z, x3 = s.w + bo.w;
+                                ((float4*)a.out)[map_sample(a, a.s_begin + s_loc)] = make_float4(1.0f / (1.0f + expf(-x0)), 1.0f / (1.0f + expf(-x1)),
+                                                                                                 1.0f / (1.0f + expf(-x2)), fmaxf(x3, 0.0f));
+                            }
+                        }
+                    }
+                    if (c < 3) asm volatile("bar.sync 12, %0;" ::"n"(NUM_WORKERS) : "memory");
                 }
             }
             tc_fence_before();
-            asm volatile("bar.sync 1, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
+            // a cold PRE tile (or the next POST tile) rewrites the whole operand region and TMEM X with all twelve warps
+            if (!has_next) asm volatile("bar.sync 1, %0;" ::"n"(NUM_OPND_WARPS * 32) : "memory");
         };
         for (long long rd = 0; rd < n_rounds; ++rd) {
             const long long tile_raw = first + rd * stride;
@@ -1024,14 +1114,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 if (tile_next >= a.n_tiles) tile_next = a.n_tiles - 1;
                 pre_tile(tile, live, rd == 0, rd + 1 < n_rounds, tile_next, rd, 0, a.early_lin ? (int)(rd & 1) : 0);
             } else if constexpr (KIND == KIND_POST) {
-                post_tile(tile, live, a.bias, a.n_blocks, 0);
+                post_tile(tile, live, a.bias, a.n_blocks, 0, false, 0, 0);
             } else {
                 // FUSED: a.n_tiles counts rounds of 64 * pts samples; PRE tile j covers samples [64 * pts * tile + j * spv, + spv)
+                // warm_rounds: TMEM half parity (j + 1) & 1, so that the last PRE tile (ppr is even) and the POST tile keep x in half 0
+                // and the next round's first lin_in goes to half 1 while the POST epilogue still reads x
                 const long long slab = (long long)blockIdx.x * ROWS * a.pts;
+                const long long next_raw = first + (rd + 1) * stride;
+                const long long tile_nr = next_raw < a.n_tiles ? next_raw : a.n_tiles - 1;
                 for (int j = 0; j < a.ppr; ++j)
-                    pre_tile(tile * a.ppr + j, live, j == 0, j + 1 < a.ppr, tile * a.ppr + j + 1, rd * a.ppr + j, slab + (long long)j * a.spv,
-                             a.early_lin ? (j & 1) : 0);
-                for (int k = 0; k < a.pts; ++k) post_tile(tile * a.pts + k, live, a.bias_post, a.n_blocks_post, slab + (long long)k * ROWS);
+                    pre_tile(tile * a.ppr + j, live, j == 0 && (rd == 0 || !a.warm_rounds), j + 1 < a.ppr, tile * a.ppr + j + 1, rd * a.ppr + j,
+                             slab + (long long)j * a.spv, a.warm_rounds ? ((j + 1) & 1) : a.early_lin ? (j & 1) : 0);
+                for (int k = 0; k < a.pts; ++k)
+                    post_tile(tile * a.pts + k, live, a.bias_post, a.n_blocks_post, slab + (long long)k * ROWS,
+                              a.warm_rounds && k + 1 == a.pts && rd + 1 < n_rounds, tile_nr * a.ppr, (rd + 1) * a.ppr);
             }
         }
     }
@@ -1068,14 +1164,14 @@ static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cu
     std::vector<int> zm[2], pre[2], post[2];
     int layer_pair0 = 0;
     // ring-use order = the MMA issue order of a step (mlp_pair_kernel): K blocks [0, nkb - tail) K-block-outer, the tail N-tile-outer
-    auto layer = [&](std::vector<int>* tab, bool par, int nkb, int n_mt, int n_tiles, int flag = 0) {
+    auto layer = [&](std::vector<int>* tab, bool par, int nkb, int n_mt, int n_tiles) {
         const int tail = n_tiles == 2 ? (t.tail_kb < nkb ? t.tail_kb : nkb) : 0, kb_split = nkb - tail;
         if (tab)
             for (int r = 0; r < 2; ++r) {
                 auto put = [&](int kb, int n2) {
                     const int pair = layer_pair0 + (2 * n2 + r) * nkb + kb;
-                    tab[r].push_back((2 * pair) | flag);
-                    if (par) tab[r].push_back((2 * pair + 1) | flag);
+                    tab[r].push_back(2 * pair);
+                    if (par) tab[r].push_back(2 * pair + 1);
                 };
                 for (int kb = 0; kb < kb_split; ++kb)
                     for (int n2 = 0; n2 < n_tiles; ++n2) put(kb, n2);
@@ -1091,7 +1187,7 @@ static cudaError_t tc2_build_tables(TcState& t, const MlpDev& m, bool parity, cu
         layer(pre, parity, kbh, 4, 2);                               // fc_1[b]
     }
     for (int b = 0; b < t.n_post; ++b) { layer(post, parity, kbh, 4, 2); layer(post, parity, kbh, 4, 2); }
-    layer(post, parity, kbh, 2, 1, t.wmap_small_ok ? TILE_SMALL : 0);   // lin_out packed as 2 M-tiles (second is zeros); 16 rows of each suffice
+    // (lin_out is not a GEMM step: the POST epilogue computes its 4 outputs on the CUDA cores from the fp32 weights)
     t.uses2_zmap = (int)zm[0].size(); t.uses2_pre = (int)pre[0].size(); t.uses2_post = (int)post[0].size();
     std::vector<int> flat;
     for (int r = 0; r < 2; ++r) flat.insert(flat.end(), zm[r].begin(), zm[r].end());
@@ -1133,7 +1229,7 @@ static cudaError_t tc2_zmap(TcState& t, const SceneDev& s, const MlpDev& m, int 
         t.zmap_bytes = need;
     }
     Args z{};
-    z.wmap = t.wmap; z.wmap_small = t.wmap_small;
+    z.wmap = t.wmap;
     z.s = s;
     z.wstream = (const uint8_t*)t.wpack;
     z.tile_table = t.table2;
@@ -1191,7 +1287,6 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     }
     Args pre{}, post{};
     pre.wmap = post.wmap = t.wmap;
-    pre.wmap_small = post.wmap_small = t.wmap_small;
     pre.s = s; pre.q = q; post.s = s; post.q = q;
     pre.wstream = post.wstream = (const uint8_t*)t.wpack;
     pre.tile_table = t.table2 + 2 * t.uses2_zmap; post.tile_table = pre.tile_table + 2 * t.uses2_pre;
@@ -1211,10 +1306,11 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
     n = 0;
     for (int b = 0; b < t.n_post; ++b) {
         post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_NET, 0, 0, tl};
-        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, 0, tl};
+        // fc_1[b]; the last one releases its K blocks to the next round's first PRE tile when that follows (FUSED, warm_rounds)
+        post.steps[n++] = GemmStep{(short)kbh, 2, 256, COL_X, 1, (short)(b + 1 < t.n_post ? 0 : 3), tl};
     }
-    post.steps[n++] = GemmStep{(short)kbh, 1, 32, COL_NET, 0, 0, 0};
     post.n_steps = n;
+    pre.w_out = post.w_out = m.w_out; pre.b_out = post.b_out = m.b_out;
     pre.NV = post.NV = NV;
     pre.NV_real = post.NV_real = s.NV;
     pre.spv = post.spv = ROWS / NV;
@@ -1250,6 +1346,9 @@ cudaError_t tc2_query(TcState& t, const SceneDev& s, const MlpDev& m, const Quer
             }
         }
         f.ppr = NV * f.pts;
+        // warm rounds: x / net swap TMEM halves from tile to tile, and the POST tile must find x in half 0 -> even tile count
+        f.warm_rounds = t.warm_rounds && (f.ppr % 2 == 0);
+        if (f.warm_rounds) f.early_lin = 1;
         f.s_begin = 0; f.n_samples = total;
         f.n_tiles = (total + (long long)ROWS * f.pts - 1) / ((long long)ROWS * f.pts);
         const long long g = ((f.n_tiles + 1) / 2) * 2;

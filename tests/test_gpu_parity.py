@@ -415,11 +415,18 @@ def test_pair_kernel_pipeline_shape_sweep(NV, SB, K, nr):
         _, rgb_t, d_t = ctx.composite(rays, z, True, 1, want_weights=False)
         assert torch.equal(rgb_t, rgb_p) and torch.equal(d_t, d_p), "tail_kb=%d changes the result" % tail
     ctx.set_option("tail_kb", 3)
-    for early, fused in ((1, 1), (1, 0), (0, 0), (0, 1)):                   # next tile's lin_in behind the last fc_1 (TMEM half ping-pong)
-        ctx.set_option("early_lin", early)
+    for early, fused, warm in ((1, 1, 0), (1, 0, 0), (0, 0, 0), (0, 1, 0), (0, 1, 1), (1, 1, 1)):
+        ctx.set_option("early_lin", early)                                  # next tile's lin_in behind the last fc_1 (TMEM half ping-pong)
         ctx.set_option("fused", fused)
-        _, rgb_t, d_t = ctx.composite(rays, z, True, 1, want_weights=False)
-        assert torch.equal(rgb_t, rgb_p) and torch.equal(d_t, d_p), "early_lin=%d fused=%d changes the result" % (early, fused)
+        ctx.set_option("warm_rounds", warm)                                 # next round's first PRE tile prepared under the POST tile
+        for pts in ((1, 2) if warm else (1,)):
+            ctx.set_option("post_tiles", pts)
+            _, rgb_t, d_t = ctx.composite(rays, z, True, 1, want_weights=False)
+            assert torch.equal(rgb_t, rgb_p) and torch.equal(d_t, d_p), \
+                "early_lin=%d fused=%d warm_rounds=%d post_tiles=%d changes the result" % (early, fused, warm, pts)
+        ctx.set_option("post_tiles", 1)
+    _, rgb_s2, _ = ctx.composite(rays, z, True, 2, want_weights=False)      # fast mode through the warm-round protocol
+    assert torch.equal(rgb_s2, rgb_s)
 
 
 @pytest.mark.parametrize("backward_tc", [1, 0], ids=["tcgen05", "fp32_cuda_cores"])
