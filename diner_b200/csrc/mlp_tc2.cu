@@ -843,6 +843,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                 // x += lin_z[b](latent)  ==  x += bilinear(Y_b): gathered into the operand buffers K block by K block while the
                 // previous GEMM (lin_in / fc_1[b-1]) is still running, then added to the residual in the epilogue
                 if (b == 0 && !cold) {       // only K block 0 is left (it held the lin_in features until now)
+                    // (early_lin: handing this K block to the otherwise idle helper warps -- 4 warps instead of 8, plus a 384-thread
+                    // barrier -- was measured 2 % SLOWER end to end than letting the workers stage it themselves)
                     gather_y(a, a.zmap, wwarp, lane, Ahi, Alo, tp, 0, 0, bar_afree, ph0 & 1, ph1 & 1); ++ph0;
                 } else {
                     gather_y(a, a.zmap + (size_t)b * a.zmap_stride, wwarp, lane, Ahi, Alo, tp, 0, HID / KBLK - 1, bar_afree, ph0 & 1, ph1 & 1, a.worker_kb_hi);
@@ -974,9 +976,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
             // load x_c: W_SCALE * x_c -> TMEM X (the residual the fc_1 steps accumulate onto), relu(x_c) -> A operand
             long long smp = FUSED ? xc_row0 + r : tile * ROWS + r;          // row of the CTA's slab (FUSED) / sample of the sub-batch
             if (!FUSED && smp >= a.n_samples) smp = a.n_samples - 1;
+            // in operand halves like every epilogue (half h: this warp's 64 columns of N tile h), so that fc_0 starts on K blocks 0..3
+            // while K blocks 4..7 are still being loaded
 #pragma unroll 1
             for (int c32 = 0; c32 < (helper ? 0 : 4); ++c32) {
-                const int h0 = 256 * n2 + 128 * (q >> 1) + 32 * c32;
+                const int tcol = 128 * (c32 >> 1) + 64 * n2 + 32 * (c32 & 1);                                       // column within the 256 of x
+                const int h0 = 256 * (tcol >> 7) + 128 * (q >> 1) + (tcol & 127);
                 const float4* src = (const float4*)(a.xc + (size_t)smp * HID + h0);
                 uint32_t v[32];
 #pragma unroll
@@ -985,7 +990,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     v[4 * i] = __float_as_uint(f.x * W_SCALE); v[4 * i + 1] = __float_as_uint(f.y * W_SCALE);
                     v[4 * i + 2] = __float_as_uint(f.z * W_SCALE); v[4 * i + 3] = __float_as_uint(f.w * W_SCALE);
                 }
-                tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + 128 * n2 + 32 * c32), v);
+                tmem_st32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(COL_X + tcol), v);
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     float x[8];
@@ -997,11 +1002,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mlp_
                     *(uint4*)(Ahi + off) = hi;
                     if (PARITY) *(uint4*)(Alo + off) = lo;
                 }
+                if (c32 == 1) worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                 // -> fc_0 of the first post block, K blocks 0..3
             }
-            if (!helper) {                                                                                          // -> fc_0 of the first post block
-                worker_arrive<0>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-                worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);
-            }
+            if (!helper) worker_arrive<1>(bar_opnd, leader_opnd, is_leader_cta, wwarp, lane);                       // K blocks 4..7
             for (int b = 0; b < n_blocks; ++b) {
                 const bool last = b + 1 == n_blocks;
                 if (helper && last && has_next) {    // taps of the next PRE tile (the helpers have nothing else to do in a POST tile)
