@@ -152,7 +152,10 @@ int diner_composite(diner_ctx* ctx, const float* rays, const float* z, int SB, i
  * e.g. the reference's gen_rays output: the MLP launch then walks them in 16 x 16 pixel tiles, which keeps the gathered feature
  * map lines in L2; results do not change; 0 = off; diner_render_image sets it by itself), "tail_kb" (0..4: K blocks of every GEMM step issued
  * N-tile-outer so that the first epilogue half overlaps the step's tail), "early_split" (worker/helper split of the next tile's
- * early gather), "sub_batch" (samples per PRE/POST launch pair), "rebuild_maps" (forces the next query to rebuild the hoisted
+ * early gather), "warm_rounds" (1, default: in the fused launch the next round's first per-sample-view tile is prepared under the last
+ * GEMM of the per-sample tile, so only the first tile of a launch starts cold; needs an even number of tiles per round, i.e. more
+ * than one view), "early_lin" (the next tile's lin_in is issued behind the current tile's last GEMM into the other TMEM half; implied by
+ * warm_rounds; results do not change with either), "sub_batch" (samples per PRE/POST launch pair), "rebuild_maps" (forces the next query to rebuild the hoisted
  * lin_z maps) or "latent_layout" (see diner_set_scene). */
 int diner_set_option(diner_ctx* ctx, const char* key, long long value);
 /* Reference arguments that are not per-call sizes: key = "depth_diff_max" (sample_depthguided(..., depth_diff_max=0.05),
