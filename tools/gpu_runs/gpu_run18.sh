@@ -1,3 +1,8 @@
+# N = 2 with the final kernel: sharded image == single-GPU image, bench line
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -q --timeout 300 --tb=short -s -k "backward or training" 2>&1 | grep -E "backward \(|passed|failed|FAILED|Error" | cut -c1-250
-timeout 900 python bench.py --workload train256 --steps 3 --warmup 1 > gpurun_out/r2p_bench_train256.json 2> gpurun_out/r2p_bench_train256.err; cut -c1-330 gpurun_out/r2p_bench_train256.json; tail -2 gpurun_out/r2p_bench_train256.err
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+N=$1
+timeout 300 $TR --nproc-per-node $N --master-port 2951$N tools/check_sharded_equal.py 2>&1 | tail -2 | cut -c1-300
+timeout 600 $TR --nproc-per-node $N --master-port 2952$N bench.py --gpus $N --steps 5 --warmup 3 2>/dev/null | grep "^{" > gpurun_out/r2z_bench_${N}gpu.json
+python -c "
+import json;d=json.load(open('gpurun_out/r2z_bench_${N}gpu.json'));print('N',$N,d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['stage_ms_per_step'],d['clocks'])"
