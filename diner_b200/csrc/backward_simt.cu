@@ -317,10 +317,9 @@ cudaError_t backward_simt(const SceneDev& s, const MlpDev& m, const QueryArgs& q
         BK(cudaGetLastError());
     }
     static Tc3Map map_wt, map_ap, map_zp;
-    long long pair_in = 0, pair_z[DINER_MAX_BLOCKS], pair_0[DINER_MAX_BLOCKS], pair_1[DINER_MAX_BLOCKS];   // offsets in tcs->wpack (tc_pack_weights order)
+    long long pair_z[DINER_MAX_BLOCKS], pair_0[DINER_MAX_BLOCKS], pair_1[DINER_MAX_BLOCKS];   // offsets in tcs->wpack (tc_pack_weights order)
     {
         long long p = tc::MT * 1;                                                  // lin_in
-        (void)pair_in;
         for (int b = 0; b < n_pre; ++b) { pair_z[b] = p; p += tc::MT * (L / 64); pair_0[b] = p; p += tc::MT * 8; pair_1[b] = p; p += tc::MT * 8; }
         for (int b = n_pre; b < m.n_blocks; ++b) { pair_0[b] = p; p += tc::MT * 8; pair_1[b] = p; p += tc::MT * 8; }
     }

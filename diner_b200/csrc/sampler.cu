@@ -113,11 +113,11 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
 
         // ---- occlusion-aware likelihood = lik * exclusive cumprod(1 - lik)   (:131-132)
         //      and its weighted mean / std over the candidates (torch_helpers.py:215-223)
-        float run = 1.0f, wsum = 0.0f, wz = 0.0f;
+        float run = 1.0f, wsum = 0.0f;
         bool any_nz = false;
         for (int base = 0; base < Cpad; base += 32) {
             const float l = lk[base + lane];
-            float f = 1.0f - l, inc = f;
+            float inc = 1.0f - l;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 float t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -159,7 +159,6 @@ sampler_kernel(SceneDev s, SamplerArgs a) {
                 if (pass == 0) mean = acc; else sdev = sqrtf(acc);
             }
         }
-        (void)wz;
 
         // ---- compact the non-zero-likelihood candidates (zero ones become empty slots anyway, :176-178)
         int nnz = 0;

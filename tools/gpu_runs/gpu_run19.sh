@@ -1,3 +1,5 @@
+# compute-sanitizer memcheck over the library's kernels on the smoke-sized render (parity + fast modes)
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -q --timeout 400 --tb=short -s -k "config3_size" 2>&1 | grep -E "config-3|passed|failed|FAILED|Error|assert" | cut -c1-250
-timeout 900 python bench.py --workload train256 --steps 3 --warmup 1 > gpurun_out/r2q_bench_train256.json 2> gpurun_out/r2q_bench_train256.err; cat gpurun_out/r2q_bench_train256.json | cut -c1-1500; tail -2 gpurun_out/r2q_bench_train256.err
+timeout 500 compute-sanitizer --tool memcheck --kernel-name kernel_substring=mlp_pair --kernel-name kernel_substring=sampler_kernel --kernel-name kernel_substring=composite_kernel --kernel-name kernel_substring=pack_ --print-limit 20 \
+  python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2z_memcheck.log 2>&1
+echo "rc=$?"; grep -v "^$" gpurun_out/r2z_memcheck.log | tail -12 | cut -c1-300
