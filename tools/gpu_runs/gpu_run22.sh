@@ -1,6 +1,5 @@
+# last check of the committed state: whole GPU suite + default bench line
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -4
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-timeout 600 python bench.py > gpurun_out/r2t_bench_default.json 2> gpurun_out/r2t_bench_default.err; python -c "
-import json;d=json.load(open('gpurun_out/r2t_bench_default.json'));print(d['value'],d['e2e'],d['roofline']['frac'],d['roofline']['traffic'],d['roofline']['stage_ms_per_step'],d['clocks'],d['gpu_launches'],d['parity'],d['cpu_baseline']['value'],d['gpu_eager_baseline']['value'])"
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 | cut -c1-300
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | cut -c1-300
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | grep "^{" > gpurun_out/r2zz_bench.json; python -c "
+import json;d=json.load(open('gpurun_out/r2zz_bench.json'));print(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['frac'],d['roofline']['traffic'],d['clocks'],d['gpu_launches'])"
