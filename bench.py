@@ -452,9 +452,9 @@ def main():
         pre_flops_per_launch = (FLOP_PER_SAMPLE if fused else FLOP_PRE_PER_SAMPLE) * n_samp_rank / n_pre_launches
         achieved = pre_flops_per_launch / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
         # FLOPs the kernel actually issues to the tensor pipe per sample: NV x (lin_in + 3 x (fc_0 + fc_1)) (lin_z is hoisted into
-        # the once-per-scene Y maps) [+ 2 x (fc_0 + fc_1) + lin_out (N = 32) in the fused kernel], x3 MMAs per product in parity mode
+        # the once-per-scene Y maps) [+ 2 x (fc_0 + fc_1) in the fused kernel; lin_out runs on the CUDA cores], x3 MMAs per product in parity mode
         passes = 3 if args.mode == "parity" else 1
-        exec_per_sample = NV * (2 * 64 * 512 + 6 * 2 * 512 * 512) + (4 * 2 * 512 * 512 + 2 * 512 * 32 if fused else 0)
+        exec_per_sample = NV * (2 * 64 * 512 + 6 * 2 * 512 * 512) + (4 * 2 * 512 * 512 if fused else 0)
         executed = passes * exec_per_sample * n_samp_rank / n_pre_launches / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
         tr = latest_traffic() if (args.mode == "parity" and args.workload == "dtu512") else None   # captured on this workload's shape
         e2e_d2h = (rgb_h.numel() + dep_h.numel()) * 4 if world == 1 else img_h.numel() * 4
