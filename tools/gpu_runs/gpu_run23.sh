@@ -1,6 +1,3 @@
+# launch list of one training step (config 3) with the final kernels
 cd $GRAFT_REPO_ROOT
-TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-N=$1
-timeout 600 $TR --nproc-per-node $N --master-port 2952$N bench.py --gpus $N --steps 5 --warmup 3 2>/dev/null | grep "^{" > gpurun_out/r2u_bench_${N}gpu.json
-python -c "
-import json;d=json.load(open('gpurun_out/r2u_bench_${N}gpu.json'));print('N',$N,d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['stage_ms_per_step'],d['clocks'])"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r2z_train_launches.csv python bench.py --workload train256 --steps 1 --warmup 1 > gpurun_out/r2z_ncu_train.log 2>&1; tail -1 gpurun_out/r2z_ncu_train.log | cut -c1-300
