@@ -281,15 +281,17 @@ def train_bench(args):
                       "loss": float(loss), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "grad_check": grad_check}))
 
 
-def latest_traffic():
-    """dram bytes per PRE launch from the newest committed ncu --set full summary (profiles/*_traffic.json, written by
-    tools/ncu_summary.py from the .ncu-rep of the same kernel); None when there is none."""
+def latest_traffic(workload="dtu512"):
+    """dram bytes per launch from the newest committed ncu --set full summary of this workload's shape (profiles/*_traffic.json,
+    written by tools/ncu_summary.py from the .ncu-rep of the same kernel; `workload` / `samples` say what was captured); None when
+    there is none."""
     import glob
     best = None
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
         try:
             d = json.load(open(f))
-            best = dict(d, file=os.path.relpath(f, ROOT))
+            if d.get("workload", "dtu512") == workload:
+                best = dict(d, file=os.path.relpath(f, ROOT))
         except Exception:
             pass
     return best
@@ -456,7 +458,7 @@ def main():
         passes = 3 if args.mode == "parity" else 1
         exec_per_sample = NV * (2 * 64 * 512 + 6 * 2 * 512 * 512) + (4 * 2 * 512 * 512 if fused else 0)
         executed = passes * exec_per_sample * n_samp_rank / n_pre_launches / (pre_ms_per_launch * 1e-3) / 1e12 if pre_ms_per_launch else 0.0
-        tr = latest_traffic() if (args.mode == "parity" and args.workload == "dtu512") else None   # captured on this workload's shape
+        tr = latest_traffic(args.workload) if args.mode == "parity" else None                    # captured on this workload's shape
         e2e_d2h = (rgb_h.numel() + dep_h.numel()) * 4 if world == 1 else img_h.numel() * 4
         line = {
             "metric": "rays_per_sec", "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -486,8 +488,8 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the newest ncu --set full capture.  The capture
                          # launches the kernel on a 524 288-sample slab of this workload (ncu replays every launch ~40 times); this run's
                          # launch covers n_samp_rank samples, so the captured bytes are scaled by the sample ratio
-                         "traffic": tr["dram_bytes_per_launch"] * n_samp_rank / n_pre_launches / 524288.0 if tr else None,
-                         "traffic_captured": {"bytes": tr["dram_bytes_per_launch"], "samples": 524288} if tr else None,
+                         "traffic": tr["dram_bytes_per_launch"] * n_samp_rank / n_pre_launches / float(tr.get("samples", 524288)) if tr else None,
+                         "traffic_captured": {"bytes": tr["dram_bytes_per_launch"], "samples": tr.get("samples", 524288)} if tr else None,
                          "traffic_source": ("ncu --set full, %s" % tr["file"]) if tr else None,
                          "whole_step_frac": rays_per_s / world * K * FLOP_PER_SAMPLE / 1e12 / pk["sustained"],
                          "stage_ms_per_step": stage,
