@@ -81,3 +81,13 @@ def test_bench_sample_indices_in_range():
         p = bench.strided_pick(n)
         assert p.numel() == n and int(p.min()) >= 0 and int(p.max()) < bench.H * bench.W
         assert p.unique().numel() == n
+
+
+def test_bench_traffic_summary_matches_workload():
+    """roofline.traffic comes from the ncu summary captured on the SAME workload shape (profiles/*_traffic.json carry it)."""
+    import bench
+    d = bench.latest_traffic("dtu512")
+    s = bench.latest_traffic("stress1024")
+    assert d and d.get("workload", "dtu512") == "dtu512" and d.get("samples", 524288) == 524288
+    assert s and s["workload"] == "stress1024" and s["samples"] == 16384 * 256
+    assert bench.latest_traffic("no-such-workload") is None
